@@ -1,0 +1,440 @@
+"""ctypes bindings for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+* ``liboracle.so``      -- plain-C restatement of the hot path (bx_oracle.c)
+* ``_ref/libbxref.so``  -- the unmodified reference compiled by oracle/Makefile
+                           (present in the build container; travels to the GPU
+                           box as a prebuilt file)
+
+Only tests/, ``__graft_entry__.smoke()`` and the cpu_baseline / ``--impl
+reference`` legs of bench.py import this module.  The product package
+``baryonyx_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = "/root/reference"
+
+
+class Params(C.Structure):
+    """Mirror of baryonyx::solver_parameters (lib/include/baryonyx/core:294-462).
+
+    Same layout for ``ox_params`` (bx_oracle.h), ``bxref_params`` (bxref.h) and
+    ``bxg_params`` (include/bxg.h).
+    """
+
+    _fields_ = [
+        ("time_limit", C.c_double),
+        ("theta", C.c_double),
+        ("delta", C.c_double),
+        ("kappa_min", C.c_double),
+        ("kappa_step", C.c_double),
+        ("kappa_max", C.c_double),
+        ("alpha", C.c_double),
+        ("pushing_k_factor", C.c_double),
+        ("pushing_objective_amplifier", C.c_double),
+        ("init_policy_random", C.c_double),
+        ("init_crossover_bastert_insertion", C.c_double),
+        ("init_crossover_solution_selection_mean", C.c_double),
+        ("init_crossover_solution_selection_stddev", C.c_double),
+        ("init_mutation_variable_mean", C.c_double),
+        ("init_mutation_variable_stddev", C.c_double),
+        ("init_mutation_value_mean", C.c_double),
+        ("init_mutation_value_stddev", C.c_double),
+        ("init_kappa_improve_start", C.c_double),
+        ("init_kappa_improve_increase", C.c_double),
+        ("init_kappa_improve_stop", C.c_double),
+        ("w", C.c_double),
+        ("seed", C.c_uint32),
+        ("thread", C.c_int32),
+        ("limit", C.c_int64),
+        ("print_level", C.c_int32),
+        ("pushes_limit", C.c_int32),
+        ("pushing_iteration_limit", C.c_int32),
+        ("init_population_size", C.c_int32),
+        ("pre_order", C.c_int32),
+        ("order", C.c_int32),
+        ("float_type", C.c_int32),
+        ("init_policy", C.c_int32),
+        ("cost_norm", C.c_int32),
+        ("mode", C.c_int32),
+        ("preprocessor", C.c_int32),
+        ("observer", C.c_int32),
+        ("storage", C.c_int32),
+        ("solver", C.c_int32),
+        ("debug", C.c_int32),
+    ]
+
+    def copy(self) -> "Params":
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+ORDERS = {
+    "none": 0,
+    "reversing": 1,
+    "random-sorting": 2,
+    "infeasibility-decr": 3,
+    "infeasibility-incr": 4,
+    "lagrangian-decr": 5,
+    "lagrangian-incr": 6,
+    "pi-sign-change": 7,
+    "cycle": 8,
+}
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile liboracle.so (gcc) if missing or stale; returns its path."""
+    so = os.path.join(HERE, "liboracle.so")
+    src = [os.path.join(HERE, f) for f in ("bx_oracle.c", "bx_oracle.h")]
+    if force or not os.path.exists(so) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in src
+    ):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"])
+    return so
+
+
+def build_ref() -> str | None:
+    """Compile _ref/libbxref*.so from /root/reference when it is present."""
+    so = os.path.join(HERE, "_ref", "libbxref.so")
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "src")):
+        subprocess.check_call(["make", "-C", HERE, "-j", str(os.cpu_count() or 4), "ref"])
+    return so if os.path.exists(so) else None
+
+
+# --------------------------------------------------------------------------
+# liboracle.so
+# --------------------------------------------------------------------------
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    lib = C.CDLL(build_oracle())
+    lib.ox_default_params.argtypes = [C.POINTER(Params)]
+    lib.ox_clamp_params.argtypes = [C.POINTER(Params), C.POINTER(Params)]
+    lib.ox_minstd_next.argtypes = [C.POINTER(C.c_uint32)]
+    lib.ox_minstd_next.restype = C.c_uint32
+    lib.ox_bernoulli.argtypes = [C.c_double, C.POINTER(C.c_uint32)]
+    lib.ox_uniform_u64.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.ox_uniform_u64.restype = C.c_uint64
+    lib.ox_shuffle_int.argtypes = [_i32p, C.c_int, C.POINTER(C.c_uint32)]
+    lib.ox_sort_rc.argtypes = [_f64p, _i32p, C.c_int, C.c_int]
+    lib.ox_sort_pairs.argtypes = [_i32p, _i32p, C.c_int, C.c_int]
+    lib.ox_normal.argtypes = [C.c_double, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32)]
+    lib.ox_problem_create.argtypes = [
+        C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int, C.c_int,
+        C.c_int, _i32p, _f64p, C.c_double,
+    ]
+    lib.ox_problem_create.restype = C.c_void_p
+    lib.ox_problem_destroy.argtypes = [C.c_void_p]
+    lib.ox_problem_set_tail_value.argtypes = [C.c_void_p, C.c_double]
+    lib.ox_which_problem_type.argtypes = [C.c_int, _i32p, C.c_int]
+    lib.ox_run_begin.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32]
+    lib.ox_run_begin.restype = C.c_void_p
+    lib.ox_run_end.argtypes = [C.c_void_p]
+    lib.ox_run_info.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ox_run_sweep.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.ox_run_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.ox_run_set_x.argtypes = [C.c_void_p, _u64p]
+    lib.ox_run_set_rng.argtypes = [C.c_void_p, C.c_uint32]
+    lib.ox_run_objective.argtypes = [C.c_void_p]
+    lib.ox_run_objective.restype = C.c_double
+    lib.ox_run_updates.argtypes = [C.c_void_p]
+    lib.ox_run_updates.restype = C.c_int64
+    lib.ox_solve.argtypes = [
+        C.c_void_p, C.POINTER(Params), C.c_uint32, _i8p, C.POINTER(C.c_double),
+        C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+    ]
+    lib.ox_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
+    lib.ox_exhaustive_solve.argtypes = [C.c_int, _i32p, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
+    _oracle = lib
+    return lib
+
+
+def default_params() -> Params:
+    p = Params()
+    oracle().ox_default_params(C.byref(p))
+    return p
+
+
+def clamp_params(p: Params) -> Params:
+    q = Params()
+    oracle().ox_clamp_params(C.byref(p), C.byref(q))
+    return q
+
+
+class _RunBase:
+    """Common state accessors for step-level runs (oracle and reference)."""
+
+    def __init__(self, m, n, nnz):
+        self.m, self.n, self.nnz = m, n, nnz
+        self.words = n // 64 + 1
+
+    def state(self, order_cap=None):
+        x = np.zeros(self.words, np.uint64)
+        pi = np.zeros(self.m, np.float64)
+        P = np.zeros(self.nnz, np.float64)
+        rng = C.c_uint32(0)
+        cap = order_cap or (2 * max(self.m, self.n) + 2)
+        ol = np.zeros(cap, np.int32)
+        on = C.c_int(0)
+        self._state(_opt(x), _opt(pi), _opt(P), C.cast(C.byref(rng), C.c_void_p),
+                    _opt(ol), C.cast(C.byref(on), C.c_void_p), None)
+        return {"x": x, "pi": pi, "P": P, "rng": rng.value, "order": ol, "order_len": on.value}
+
+    def norm_cost(self):
+        c = np.zeros(self.n, np.float64)
+        self._state(None, None, None, None, None, None, _opt(c))
+        return c
+
+
+class OracleProblem:
+    def __init__(self, inst):
+        """inst: dict with m, n, row_ptr, col, factor, cmin, cmax, problem_type,
+        maximize, obj_var, obj_factor, cost_constant (see baryonyx_b200.synth)."""
+        self.inst = inst
+        self.lib = oracle()
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        self.h = self.lib.ox_problem_create(
+            inst["m"], inst["n"], i32(inst["row_ptr"]), i32(inst["col"]), i32(inst["factor"]),
+            i32(inst["cmin"]), i32(inst["cmax"]), int(inst["problem_type"]), int(inst["maximize"]),
+            len(inst["obj_var"]), i32(inst["obj_var"]),
+            np.ascontiguousarray(inst["obj_factor"], np.float64), float(inst["cost_constant"]),
+        )
+        self.m, self.n, self.nnz = inst["m"], inst["n"], int(inst["row_ptr"][-1])
+
+    def set_tail_value(self, v: float):
+        self.lib.ox_problem_set_tail_value(self.h, float(v))
+
+    def close(self):
+        if self.h:
+            self.lib.ox_problem_destroy(self.h)
+            self.h = None
+
+    def run(self, params: Params, seed: int) -> "OracleRun":
+        return OracleRun(self, params, seed)
+
+    def solve(self, params: Params, seed: int):
+        x = np.zeros(self.n, np.int8)
+        value = C.c_double()
+        rem = C.c_int()
+        loop = C.c_int64()
+        upd = C.c_int64()
+        swp = C.c_int64()
+        st = self.lib.ox_solve(self.h, C.byref(params), seed, x, C.byref(value), C.byref(rem),
+                               C.byref(loop), C.byref(upd), C.byref(swp))
+        return {"status": st, "x": x, "value": value.value, "remaining": rem.value,
+                "loop": loop.value, "updates": upd.value, "sweeps": swp.value}
+
+
+class OracleRun(_RunBase):
+    def __init__(self, pb: OracleProblem, params: Params, seed: int):
+        super().__init__(pb.m, pb.n, pb.nnz)
+        self.lib = pb.lib
+        self.h = self.lib.ox_run_begin(pb.h, C.byref(params), seed)
+        if not self.h:
+            raise RuntimeError("ox_run_begin failed (unsupported cost_norm?)")
+        self._state = lambda *a: self.lib.ox_run_state(self.h, *a)
+
+    def info(self):
+        d, t = C.c_double(), C.c_double()
+        self.lib.ox_run_info(self.h, C.byref(d), C.byref(t))
+        return d.value, t.value
+
+    def sweep(self, kappa, push=0, obj_amp=0.0):
+        return self.lib.ox_run_sweep(self.h, push, kappa, obj_amp)
+
+    def set_x(self, words):
+        self.lib.ox_run_set_x(self.h, np.ascontiguousarray(words, np.uint64))
+
+    def set_rng(self, s):
+        self.lib.ox_run_set_rng(self.h, s)
+
+    def objective(self):
+        return self.lib.ox_run_objective(self.h)
+
+    def updates(self):
+        return self.lib.ox_run_updates(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.ox_run_end(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------
+# _ref/libbxref.so
+# --------------------------------------------------------------------------
+_ref = {}
+
+
+def ref_available(fast: bool = False) -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libbxref_fast.so" if fast else "libbxref.so"))
+
+
+def ref(fast: bool = False):
+    if fast in _ref:
+        return _ref[fast]
+    path = os.path.join(HERE, "_ref", "libbxref_fast.so" if fast else "libbxref.so")
+    lib = C.CDLL(path)
+    lib.bxref_default_params.argtypes = [C.POINTER(Params)]
+    lib.bxref_open.argtypes = [C.c_char_p, C.POINTER(Params)]
+    lib.bxref_open.restype = C.c_void_p
+    lib.bxref_close.argtypes = [C.c_void_p]
+    lib.bxref_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.bxref_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.bxref_export_rows.argtypes = [C.c_void_p, _i32p, _i32p, _i32p, _i32p, _i32p]
+    lib.bxref_export_objective.argtypes = [C.c_void_p, _i32p, _f64p]
+    lib.bxref_run_begin.argtypes = [C.c_void_p, C.c_uint32]
+    lib.bxref_run_begin.restype = C.c_void_p
+    lib.bxref_run_end.argtypes = [C.c_void_p]
+    lib.bxref_run_info.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.bxref_run_sweep.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    lib.bxref_run_tail_value.argtypes = [C.c_void_p]
+    lib.bxref_run_tail_value.restype = C.c_double
+    lib.bxref_run_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.bxref_run_set_x.argtypes = [C.c_void_p, _u64p]
+    lib.bxref_run_set_rng.argtypes = [C.c_void_p, C.c_uint32]
+    lib.bxref_run_objective.argtypes = [C.c_void_p]
+    lib.bxref_run_objective.restype = C.c_double
+    lib.bxref_solve.argtypes = [C.c_void_p, C.c_uint32, _i8p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.bxref_solve_public.argtypes = [C.c_void_p, C.c_uint32, _i8p, C.POINTER(C.c_double)]
+    lib.bxref_optimize.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_double, _i8p, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_double)]
+    lib.bxref_std_sort.argtypes = [_f64p, _i32p, C.c_int, C.c_int]
+    lib.bxref_std_sort_pairs.argtypes = [_i32p, _i32p, C.c_int, C.c_int]
+    lib.bxref_std_shuffle.argtypes = [_i32p, C.c_int, C.POINTER(C.c_uint32)]
+    lib.bxref_std_bernoulli.argtypes = [C.c_double, C.POINTER(C.c_uint32)]
+    lib.bxref_std_uniform_u64.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.bxref_std_uniform_u64.restype = C.c_uint64
+    lib.bxref_std_normal.argtypes = [C.c_double, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32)]
+    lib.bxref_std_pow.argtypes = [C.c_double, C.c_double]
+    lib.bxref_std_pow.restype = C.c_double
+    lib.bxref_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
+    lib.bxref_exhaustive_solve.argtypes = [C.c_int, _i32p, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
+    _ref[fast] = lib
+    return lib
+
+
+class RefProblem:
+    """LP file -> reference parser -> merged constraints."""
+
+    def __init__(self, lp_path: str, params: Params, fast: bool = False):
+        self.lib = ref(fast)
+        self.h = self.lib.bxref_open(lp_path.encode(), C.byref(params))
+        if not self.h:
+            raise RuntimeError(f"reference could not read {lp_path}")
+        v = [C.c_int() for _ in range(5)]
+        cc, nobj = C.c_double(), C.c_int()
+        self.lib.bxref_info(self.h, *[C.byref(a) for a in v], C.byref(cc), C.byref(nobj))
+        self.m, self.n, self.nnz, self.problem_type, self.maximize = [a.value for a in v]
+        self.cost_constant, self.n_obj = cc.value, nobj.value
+
+    def params(self) -> Params:
+        q = Params()
+        self.lib.bxref_get_params(self.h, C.byref(q))
+        return q
+
+    def instance(self) -> dict:
+        """Merged constraints + objective as arrays (the oracle / engine input)."""
+        row_ptr = np.zeros(self.m + 1, np.int32)
+        col = np.zeros(max(self.nnz, 1), np.int32)
+        fac = np.zeros(max(self.nnz, 1), np.int32)
+        cmin = np.zeros(self.m, np.int32)
+        cmax = np.zeros(self.m, np.int32)
+        self.lib.bxref_export_rows(self.h, row_ptr, col, fac, cmin, cmax)
+        ov = np.zeros(max(self.n_obj, 1), np.int32)
+        of = np.zeros(max(self.n_obj, 1), np.float64)
+        self.lib.bxref_export_objective(self.h, ov, of)
+        return {
+            "m": self.m, "n": self.n, "row_ptr": row_ptr, "col": col[: self.nnz], "factor": fac[: self.nnz],
+            "cmin": cmin, "cmax": cmax, "problem_type": self.problem_type, "maximize": self.maximize,
+            "obj_var": ov[: self.n_obj], "obj_factor": of[: self.n_obj], "cost_constant": self.cost_constant,
+        }
+
+    def run(self, seed: int) -> "RefRun":
+        return RefRun(self, seed)
+
+    def solve(self, seed: int):
+        x = np.zeros(self.n, np.int8)
+        value, rem = C.c_double(), C.c_int()
+        upd, swp = C.c_int64(), C.c_int64()
+        st = self.lib.bxref_solve(self.h, seed, x, C.byref(value), C.byref(rem), C.byref(upd), C.byref(swp))
+        return {"status": st, "x": x, "value": value.value, "remaining": rem.value,
+                "updates": upd.value, "sweeps": swp.value}
+
+    def solve_public(self, seed: int):
+        x = np.zeros(self.n, np.int8)
+        value = C.c_double()
+        st = self.lib.bxref_solve_public(self.h, seed, x, C.byref(value))
+        return {"status": st, "x": x, "value": value.value}
+
+    def optimize(self, seed: int, threads: int, time_limit: float):
+        x = np.zeros(self.n, np.int8)
+        value, rem = C.c_double(), C.c_int()
+        upd, swp, sec = C.c_int64(), C.c_int64(), C.c_double()
+        st = self.lib.bxref_optimize(self.h, seed, threads, time_limit, x, C.byref(value), C.byref(rem),
+                                     C.byref(upd), C.byref(swp), C.byref(sec))
+        return {"status": st, "x": x, "value": value.value, "remaining": rem.value,
+                "updates": upd.value, "sweeps": swp.value, "seconds": sec.value}
+
+    def close(self):
+        if self.h:
+            self.lib.bxref_close(self.h)
+            self.h = None
+
+
+class RefRun(_RunBase):
+    def __init__(self, pb: RefProblem, seed: int):
+        super().__init__(pb.m, pb.n, pb.nnz)
+        self.lib = pb.lib
+        self.h = self.lib.bxref_run_begin(pb.h, seed)
+        self._state = lambda *a: self.lib.bxref_run_state(self.h, *a)
+
+    def info(self):
+        d, t = C.c_double(), C.c_double()
+        self.lib.bxref_run_info(self.h, C.byref(d), C.byref(t))
+        return d.value, t.value
+
+    def sweep(self, kappa, push=0, obj_amp=0.0):
+        return self.lib.bxref_run_sweep(self.h, push, kappa, obj_amp)
+
+    def tail_value(self):
+        return self.lib.bxref_run_tail_value(self.h)
+
+    def set_x(self, words):
+        self.lib.bxref_run_set_x(self.h, np.ascontiguousarray(words, np.uint64))
+
+    def set_rng(self, s):
+        self.lib.bxref_run_set_rng(self.h, s)
+
+    def objective(self):
+        return self.lib.bxref_run_objective(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.bxref_run_end(self.h)
+            self.h = None

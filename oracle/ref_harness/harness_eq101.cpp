@@ -1,0 +1,10 @@
+// harness_eq101.cpp -- test infrastructure (see bxref.h).  Pulls the reference's
+// own translation unit in so that its solver class template is reachable;
+// the file is read from /root/reference/lib/src at build time, never copied.
+#include "itm-solver-equalities-101.cpp"
+
+#include "harness_solver.hpp"
+
+namespace bxref {
+BXREF_DEFINE(eq101, solver_equalities_101coeff)
+}
