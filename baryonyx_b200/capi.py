@@ -1,0 +1,294 @@
+"""ctypes binding of the C ABI (include/bxg.h) -- the call path of the tests and
+of bench.py.  Loads the in-tree ``libbaryonyx_b200.so`` and fails loudly when
+it is missing: the engine has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbaryonyx_b200.so")
+
+
+class Params(C.Structure):
+    """bxg_params: POD mirror of baryonyx::solver_parameters
+    (lib/include/baryonyx/core:294-462)."""
+
+    _fields_ = [
+        ("time_limit", C.c_double),
+        ("theta", C.c_double),
+        ("delta", C.c_double),
+        ("kappa_min", C.c_double),
+        ("kappa_step", C.c_double),
+        ("kappa_max", C.c_double),
+        ("alpha", C.c_double),
+        ("pushing_k_factor", C.c_double),
+        ("pushing_objective_amplifier", C.c_double),
+        ("init_policy_random", C.c_double),
+        ("init_crossover_bastert_insertion", C.c_double),
+        ("init_crossover_solution_selection_mean", C.c_double),
+        ("init_crossover_solution_selection_stddev", C.c_double),
+        ("init_mutation_variable_mean", C.c_double),
+        ("init_mutation_variable_stddev", C.c_double),
+        ("init_mutation_value_mean", C.c_double),
+        ("init_mutation_value_stddev", C.c_double),
+        ("init_kappa_improve_start", C.c_double),
+        ("init_kappa_improve_increase", C.c_double),
+        ("init_kappa_improve_stop", C.c_double),
+        ("w", C.c_double),
+        ("seed", C.c_uint32),
+        ("thread", C.c_int32),
+        ("limit", C.c_int64),
+        ("print_level", C.c_int32),
+        ("pushes_limit", C.c_int32),
+        ("pushing_iteration_limit", C.c_int32),
+        ("init_population_size", C.c_int32),
+        ("pre_order", C.c_int32),
+        ("order", C.c_int32),
+        ("float_type", C.c_int32),
+        ("init_policy", C.c_int32),
+        ("cost_norm", C.c_int32),
+        ("mode", C.c_int32),
+        ("preprocessor", C.c_int32),
+        ("observer", C.c_int32),
+        ("storage", C.c_int32),
+        ("solver", C.c_int32),
+        ("debug", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = [
+    "bxg_version", "bxg_last_error", "bxg_device_count", "bxg_default_params", "bxg_clamp_params",
+    "bxg_problem_create", "bxg_problem_destroy", "bxg_problem_info", "bxg_which_problem_type",
+    "bxg_batch_create", "bxg_batch_destroy", "bxg_batch_info", "bxg_batch_set_tail_value",
+    "bxg_batch_begin", "bxg_batch_get_state", "bxg_batch_set_state", "bxg_batch_sweep",
+    "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
+    "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_last_ms", "bxg_batch_launches",
+    "bxg_batch_words32", "bxg_batch_begin_device",
+]
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+class BxgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bxg error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """The loaded C ABI.  Raises when the native library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m baryonyx_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.bxg_last_error.restype = C.c_char_p
+    L.bxg_default_params.argtypes = [C.POINTER(Params)]
+    L.bxg_default_params.restype = None
+    L.bxg_clamp_params.argtypes = [C.POINTER(Params), C.POINTER(Params)]
+    L.bxg_clamp_params.restype = None
+    L.bxg_problem_create.argtypes = [
+        C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, _f64p,
+        C.c_double, C.c_int, C.POINTER(C.c_void_p),
+    ]
+    L.bxg_problem_destroy.argtypes = [C.c_void_p]
+    L.bxg_problem_destroy.restype = None
+    L.bxg_problem_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
+    L.bxg_which_problem_type.argtypes = [C.c_int, _i32p, C.c_int]
+    L.bxg_batch_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
+    L.bxg_batch_destroy.argtypes = [C.c_void_p]
+    L.bxg_batch_destroy.restype = None
+    L.bxg_batch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.bxg_batch_set_tail_value.argtypes = [C.c_void_p, C.c_double]
+    L.bxg_batch_begin.argtypes = [C.c_void_p, _u32p, C.c_int]
+    L.bxg_batch_get_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+    L.bxg_batch_set_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.bxg_batch_sweep.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_double, C.c_void_p]
+    L.bxg_batch_objective.argtypes = [C.c_void_p, _f64p]
+    L.bxg_batch_solve.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    L.bxg_batch_best.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.bxg_batch_argbest.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.bxg_batch_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_double)]
+    L.bxg_batch_reset_counters.argtypes = [C.c_void_p]
+    L.bxg_batch_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.bxg_batch_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.bxg_batch_words32.argtypes = [C.c_void_p]
+    L.bxg_batch_begin_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise BxgError(rc, lib().bxg_last_error().decode())
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().bxg_default_params(C.byref(p))
+    return p
+
+
+def clamp_params(p: Params) -> Params:
+    q = Params()
+    lib().bxg_clamp_params(C.byref(p), C.byref(q))
+    return q
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Problem:
+    """bxg_problem: merged constraints (CSR) + objective, resident on one GPU."""
+
+    def __init__(self, inst: dict, device: int = 0):
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        self.inst = inst
+        self.h = C.c_void_p()
+        obj_var = i32(inst["obj_var"]) if len(inst["obj_var"]) else np.zeros(1, np.int32)
+        obj_fac = (np.ascontiguousarray(inst["obj_factor"], np.float64) if len(inst["obj_factor"])
+                   else np.zeros(1, np.float64))
+        check(lib().bxg_problem_create(
+            int(inst["m"]), int(inst["n"]), i32(inst["row_ptr"]), i32(inst["col"]), i32(inst["factor"]),
+            i32(inst["cmin"]), i32(inst["cmax"]), int(inst["problem_type"]), int(inst["maximize"]),
+            len(inst["obj_var"]), obj_var, obj_fac, float(inst["cost_constant"]), device, C.byref(self.h),
+        ))
+        self.m, self.n = int(inst["m"]), int(inst["n"])
+        self.nnz = int(inst["row_ptr"][-1])
+        self.device = device
+
+    def batch(self, n_lanes: int, params: Params) -> "Batch":
+        return Batch(self, n_lanes, params)
+
+    def close(self):
+        if self.h:
+            lib().bxg_problem_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Batch:
+    """bxg_batch: n_lanes independent Solver instances (P, pi, x, rng, order)."""
+
+    def __init__(self, pb: Problem, n_lanes: int, params: Params):
+        self.pb = pb
+        self.n_lanes = n_lanes
+        self.params = params
+        self.h = C.c_void_p()
+        check(lib().bxg_batch_create(pb.h, n_lanes, C.byref(params), C.byref(self.h)))
+        self.words = pb.n // 64 + 1
+
+    def info(self):
+        nl, d, t, nb = C.c_int(), C.c_double(), C.c_double(), C.c_int64()
+        check(lib().bxg_batch_info(self.h, C.byref(nl), C.byref(d), C.byref(t), C.byref(nb)))
+        return {"n_lanes": nl.value, "delta": d.value, "theta": t.value, "device_bytes": nb.value}
+
+    def set_tail_value(self, v: float):
+        check(lib().bxg_batch_set_tail_value(self.h, float(v)))
+
+    def begin(self, seeds, reset_solver: bool = True):
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        assert len(seeds) == self.n_lanes
+        check(lib().bxg_batch_begin(self.h, seeds, int(reset_solver)))
+
+    def begin_device(self, d_x0_ptr: int, d_rng_ptr: int, reset_solver: bool = True):
+        check(lib().bxg_batch_begin_device(self.h, C.c_void_p(d_x0_ptr), C.c_void_p(d_rng_ptr),
+                                           int(reset_solver)))
+
+    def words32(self) -> int:
+        return lib().bxg_batch_words32(self.h)
+
+    def state(self, lane: int = 0):
+        pb = self.pb
+        x = np.zeros(self.words, np.uint64)
+        pi = np.zeros(pb.m, np.float64)
+        P = np.zeros(max(pb.nnz, 1), np.float64)
+        rng = C.c_uint32()
+        ol = np.zeros(2 * max(pb.m, pb.n) + 2, np.int32)
+        on = C.c_int()
+        check(lib().bxg_batch_get_state(self.h, lane, _ptr(x), _ptr(pi), _ptr(P),
+                                        C.cast(C.byref(rng), C.c_void_p), _ptr(ol),
+                                        C.cast(C.byref(on), C.c_void_p), None))
+        return {"x": x, "pi": pi, "P": P[: pb.nnz], "rng": rng.value, "order": ol, "order_len": on.value}
+
+    def norm_cost(self):
+        c = np.zeros(self.pb.n, np.float64)
+        check(lib().bxg_batch_get_state(self.h, 0, None, None, None, None, None, None, _ptr(c)))
+        return c
+
+    def set_state(self, lane, x_words=None, pi=None, P=None, rng=None):
+        xw = None if x_words is None else np.ascontiguousarray(x_words, np.uint64)
+        pi_ = None if pi is None else np.ascontiguousarray(pi, np.float64)
+        P_ = None if P is None else np.ascontiguousarray(P, np.float64)
+        r = None if rng is None else C.c_uint32(rng)
+        check(lib().bxg_batch_set_state(self.h, lane, _ptr(xw), _ptr(pi_), _ptr(P_),
+                                        None if r is None else C.cast(C.byref(r), C.c_void_p)))
+
+    def sweep(self, kappa, push: int = 0, obj_amp: float = 0.0):
+        k = np.ascontiguousarray(np.broadcast_to(np.asarray(kappa, np.float64), (self.n_lanes,)))
+        rem = np.zeros(self.n_lanes, np.int32)
+        check(lib().bxg_batch_sweep(self.h, int(push), k, float(obj_amp), _ptr(rem)))
+        return rem
+
+    def objective(self):
+        v = np.zeros(self.n_lanes, np.float64)
+        check(lib().bxg_batch_objective(self.h, v))
+        return v
+
+    def solve(self):
+        st = np.zeros(self.n_lanes, np.int32)
+        val = np.zeros(self.n_lanes, np.float64)
+        rem = np.zeros(self.n_lanes, np.int32)
+        loop = np.zeros(self.n_lanes, np.int64)
+        check(lib().bxg_batch_solve(self.h, _ptr(st), _ptr(val), _ptr(rem), _ptr(loop)))
+        return {"status": st, "value": val, "remaining": rem, "loop": loop}
+
+    def best(self, lane: int):
+        x = np.zeros(self.pb.n, np.int8)
+        check(lib().bxg_batch_best(self.h, lane, _ptr(x)))
+        return x
+
+    def argbest(self):
+        l, v, r = C.c_int(), C.c_double(), C.c_int()
+        check(lib().bxg_batch_argbest(self.h, C.byref(l), C.byref(v), C.byref(r)))
+        return l.value, v.value, r.value
+
+    def counters(self):
+        u, s, b = C.c_int64(), C.c_int64(), C.c_double()
+        check(lib().bxg_batch_counters(self.h, C.byref(u), C.byref(s), C.byref(b)))
+        return {"updates": u.value, "sweeps": s.value, "algorithmic_bytes": b.value}
+
+    def reset_counters(self):
+        check(lib().bxg_batch_reset_counters(self.h))
+
+    def last_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().bxg_batch_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        check(lib().bxg_batch_launches(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().bxg_batch_destroy(self.h)
+            self.h = C.c_void_p()

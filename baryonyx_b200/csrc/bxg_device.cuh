@@ -1,0 +1,332 @@
+// bxg_device.cuh -- device-side building blocks of the sweep engine.
+//
+// Deterministic fp64 mode: every floating-point operation that feeds a result
+// is written with the round-to-nearest intrinsics (__dadd_rn, __dmul_rn,
+// __ddiv_rn), which the compiler never contracts into FMAs, and the file is
+// compiled with -fmad=false as a second guard.  The reference side of the
+// parity tests is built with -ffp-contract=off for the same reason
+// (SURVEY.md 8c).
+//
+// The random stream and the orderings are those of the C++ standard library
+// the reference runs on (libstdc++ 13): std::default_random_engine =
+// minstd_rand0 (bits/random.h:1592-1641), bernoulli_distribution on
+// generate_canonical<double,53> (random.tcc:3349-3381),
+// uniform_int_distribution (uniform_int_dist.h:284-373), std::shuffle
+// (stl_algo.h:3738-3803) and std::sort (stl_algo.h:1810-1957).
+#ifndef BXG_DEVICE_CUH
+#define BXG_DEVICE_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bxg {
+
+// ---------------------------------------------------------------------------
+// minstd_rand0: s <- 16807 s mod (2^31 - 1)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t
+mod_m31(uint64_t x)
+{
+    // x < 2^62: two Mersenne folds, one conditional subtract
+    x = (x & 0x7fffffffull) + (x >> 31);
+    x = (x & 0x7fffffffull) + (x >> 31);
+    return x >= 0x7fffffffull ? (uint32_t)(x - 0x7fffffffull) : (uint32_t)x;
+}
+
+__host__ __device__ __forceinline__ uint32_t
+lcg_mul(uint32_t s, uint32_t a)
+{
+    return mod_m31((uint64_t)s * a);
+}
+
+__host__ __device__ __forceinline__ uint32_t
+lcg_next(uint32_t& s)
+{
+    s = lcg_mul(s, 16807u);
+    return s;
+}
+
+// 16807^k mod (2^31 - 1)
+__host__ __device__ inline uint32_t
+lcg_pow(uint64_t k)
+{
+    uint32_t r = 1u, b = 16807u;
+    while (k) {
+        if (k & 1)
+            r = lcg_mul(r, b);
+        b = lcg_mul(b, b);
+        k >>= 1;
+    }
+    return r;
+}
+
+// generate_canonical<double,53> from two successive engine outputs
+__device__ __forceinline__ double
+canonical_from(uint32_t g1, uint32_t g2)
+{
+    const double r = 2147483646.0;
+    const double rr = 2147483646.0 * 2147483646.0; // rounded once, like tmp*=r
+    double sum = __dadd_rn((double)(g1 - 1u), __dmul_rn((double)(g2 - 1u), r));
+    double ret = __ddiv_rn(sum, rr);
+    if (ret >= 1.0)
+        ret = 0.99999999999999988897769753748; // nextafter(1.0, 0.0)
+    return ret;
+}
+
+__device__ __forceinline__ bool
+bernoulli(uint32_t& s, double p)
+{
+    const uint32_t g1 = lcg_next(s);
+    const uint32_t g2 = lcg_next(s);
+    return canonical_from(g1, g2) < p;
+}
+
+// uniform_int_distribution<unsigned long>{0, b} for b < 2147483645
+__device__ __forceinline__ uint32_t
+uniform_below(uint32_t& s, uint32_t b)
+{
+    const uint32_t urngrange = 2147483645u;
+    const uint32_t uerange = b + 1u;
+    const uint32_t scaling = urngrange / uerange;
+    const uint32_t past = uerange * scaling;
+    uint32_t ret;
+    do
+        ret = lcg_next(s) - 1u;
+    while (ret >= past);
+    return ret / scaling;
+}
+
+// ---------------------------------------------------------------------------
+// std::shuffle, executed by ONE thread on an array view.
+// ---------------------------------------------------------------------------
+template<typename T>
+__device__ inline void
+seq_shuffle(T* a, int n, uint32_t& s)
+{
+    if (n <= 1)
+        return;
+
+    if (2147483645u / (uint32_t)n >= (uint32_t)n) {
+        int i = 1;
+        if ((n % 2) == 0) {
+            const uint32_t j = uniform_below(s, 1u);
+            T t = a[i];
+            a[i] = a[j];
+            a[j] = t;
+            ++i;
+        }
+        while (i != n) {
+            const uint32_t swap_range = (uint32_t)i + 1u;
+            const uint32_t b1 = swap_range + 1u;
+            const uint32_t x = uniform_below(s, swap_range * b1 - 1u);
+            uint32_t j = x / b1;
+            T t = a[i];
+            a[i] = a[j];
+            a[j] = t;
+            ++i;
+            j = x % b1;
+            t = a[i];
+            a[i] = a[j];
+            a[j] = t;
+            ++i;
+        }
+        return;
+    }
+
+    for (int i = 1; i != n; ++i) {
+        const uint32_t j = uniform_below(s, (uint32_t)i);
+        T t = a[i];
+        a[i] = a[j];
+        a[j] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// std::sort (introsort + final insertion sort), executed by ONE thread.
+// Less is a functor bool(const T&, const T&).
+// ---------------------------------------------------------------------------
+template<typename T, typename Less>
+__device__ inline void
+seq_unguarded_linear_insert(T* a, int last, Less less)
+{
+    T val = a[last];
+    int next = last - 1;
+    while (less(val, a[next])) {
+        a[last] = a[next];
+        last = next;
+        --next;
+    }
+    a[last] = val;
+}
+
+template<typename T, typename Less>
+__device__ inline void
+seq_insertion_sort(T* a, int first, int last, Less less)
+{
+    if (first == last)
+        return;
+    for (int i = first + 1; i != last; ++i) {
+        if (less(a[i], a[first])) {
+            T val = a[i];
+            for (int j = i; j > first; --j)
+                a[j] = a[j - 1];
+            a[first] = val;
+        } else
+            seq_unguarded_linear_insert(a, i, less);
+    }
+}
+
+template<typename T, typename Less>
+__device__ inline void
+seq_push_heap(T* a, int first, int hole, int top, const T& value, Less less)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && less(a[first + parent], value)) {
+        a[first + hole] = a[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    a[first + hole] = value;
+}
+
+template<typename T, typename Less>
+__device__ inline void
+seq_adjust_heap(T* a, int first, int hole, int len, const T& value, Less less)
+{
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (less(a[first + second], a[first + (second - 1)]))
+            second--;
+        a[first + hole] = a[first + second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        a[first + hole] = a[first + (second - 1)];
+        hole = second - 1;
+    }
+    seq_push_heap(a, first, hole, top, value, less);
+}
+
+template<typename T, typename Less>
+__device__ inline void
+seq_heap_sort(T* a, int first, int last, Less less)
+{
+    const int len = last - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        for (;;) {
+            T value = a[first + parent];
+            seq_adjust_heap(a, first, parent, len, value, less);
+            if (parent == 0)
+                break;
+            parent--;
+        }
+    }
+    while (last - first > 1) {
+        --last;
+        T value = a[last];
+        a[last] = a[first];
+        seq_adjust_heap(a, first, 0, last - first, value, less);
+    }
+}
+
+template<typename T, typename Less>
+__device__ inline void
+seq_move_median_to_first(T* a, int result, int ia, int ib, int ic, Less less)
+{
+    int pick;
+    if (less(a[ia], a[ib])) {
+        if (less(a[ib], a[ic]))
+            pick = ib;
+        else if (less(a[ia], a[ic]))
+            pick = ic;
+        else
+            pick = ia;
+    } else if (less(a[ia], a[ic]))
+        pick = ia;
+    else if (less(a[ib], a[ic]))
+        pick = ic;
+    else
+        pick = ib;
+    T t = a[result];
+    a[result] = a[pick];
+    a[pick] = t;
+}
+
+template<typename T, typename Less>
+__device__ inline int
+seq_unguarded_partition(T* a, int first, int last, int pivot, Less less)
+{
+    for (;;) {
+        while (less(a[first], a[pivot]))
+            ++first;
+        --last;
+        while (less(a[pivot], a[last]))
+            --last;
+        if (!(first < last))
+            return first;
+        T t = a[first];
+        a[first] = a[last];
+        a[last] = t;
+        ++first;
+    }
+}
+
+// Explicit stack instead of recursion: the reference recurses on the right
+// part and loops on the left; sub-ranges are disjoint, so order is free.
+template<typename T, typename Less>
+__device__ inline void
+seq_std_sort(T* a, int n, Less less)
+{
+    if (n <= 1)
+        return;
+
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1)
+        ++lg;
+
+    // each pending entry: first, last, depth_limit
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    stack_first[0] = 0;
+    stack_last[0] = n;
+    stack_depth[0] = lg * 2;
+    sp = 1;
+
+    while (sp) {
+        --sp;
+        int first = stack_first[sp];
+        int last = stack_last[sp];
+        int depth = stack_depth[sp];
+
+        while (last - first > 16) {
+            if (depth == 0) {
+                seq_heap_sort(a, first, last, less);
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            seq_move_median_to_first(a, first, first + 1, mid, last - 1, less);
+            const int cut = seq_unguarded_partition(a, first + 1, last, first, less);
+            stack_first[sp] = cut;
+            stack_last[sp] = last;
+            stack_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+
+    if (n > 16) {
+        seq_insertion_sort(a, 0, 16, less);
+        for (int i = 16; i != n; ++i)
+            seq_unguarded_linear_insert(a, i, less);
+    } else
+        seq_insertion_sort(a, 0, n, less);
+}
+
+} // namespace bxg
+
+#endif

@@ -1,0 +1,161 @@
+// bxg_kernels.cuh -- device data layout and kernel entry points.
+#ifndef BXG_KERNELS_CUH
+#define BXG_KERNELS_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bxg {
+
+enum
+{
+    FAM_01 = 0,
+    FAM_101 = 1,
+    FAM_Z = 2
+};
+
+enum
+{
+    ORDER_NONE = 0,
+    ORDER_REVERSING,
+    ORDER_RANDOM_SORTING,
+    ORDER_INFEASIBILITY_DECR,
+    ORDER_INFEASIBILITY_INCR,
+    ORDER_LAGRANGIAN_DECR,
+    ORDER_LAGRANGIAN_INCR,
+    ORDER_PI_SIGN_CHANGE,
+    ORDER_CYCLE
+};
+
+enum
+{
+    Z_BRANCH_AND_BOUND = 0,
+    Z_EXHAUSTIVE,
+    Z_UNCONSTRAINED_BRANCH_AND_BOUND,
+    Z_UNCONSTRAINED_EXHAUSTIVE,
+    Z_LINEAR
+};
+
+// Reduced-cost element: the union of the three solvers' rc_data
+// (itm-solver-inequalities-01.cpp:40-54, -101.cpp:41-56, -Z.cpp:44-59).
+struct __align__(16) RC
+{
+    double value;
+    int id;
+    int f;
+};
+
+// Read-only structure shared by all lanes.  P lives in CSC order (see
+// DESIGN.md): the gather for column j reads P[col_ptr[j] .. col_ptr[j+1])
+// contiguously, and the row's own entry is one of those.
+struct DevProblem
+{
+    int m, n, nnz, max_row;
+    int family, maximize;
+    int xw32; // 32-bit words per x vector = 2 * (n/64 + 1)
+    int n_obj;
+    int obj_any_order; // objective sums are exact in any order
+    int need_z;
+    double cost_constant;
+
+    const int* row_ptr;    // [m+1]
+    const int* row_col;    // [nnz] column of each row element
+    const int* row_cscpos; // [nnz] position of the element in CSC order
+    const int* row_a;      // [nnz] factor (101/Z) or nullptr
+    const int* col_ptr;    // [n+1]
+    const int* csc_row;    // [nnz] row of each column entry, ascending
+    const int* csc_a;      // [nnz] factor in CSC order (101/Z) or nullptr
+    const int* bmin;       // [m]
+    const int* bmax;       // [m]
+    const int* row_neg;    // [m] number of negative factors (101) or nullptr
+    const float* row_bytes; // [m] algorithmic bytes of one update
+    const int* ztype;      // [m] (Z) or nullptr
+    const int* ex_start;   // [m] offset into ex_flat (Z)
+    const int* ex_count;   // [m] number of patterns (Z)
+    const int* ex_flat;    // patterns (Z)
+    const int* obj_var;    // [n_obj]
+    const double* obj_factor; // [n_obj]
+};
+
+// Per-batch parameters (uniform over lanes).
+struct DevParams
+{
+    double theta, delta;
+    double kappa_min, kappa_step, kappa_max;
+    double pushing_k_factor, pushing_objective_amplifier;
+    double w; // clamped: a sweep count
+    long long limit;
+    int pushes_limit, pushing_iteration_limit;
+    int order; // constraint_order as configured (may be ORDER_CYCLE)
+    double tail_value;
+    const double* cost;   // [n] normalised costs
+    const double* powtab; // [m+1] pow(k/m, alpha), computed by glibc on the host
+};
+
+// Per-lane control block.
+struct LaneCtl
+{
+    uint32_t rng;
+    int order_state; // current order (cycles when order == ORDER_CYCLE)
+    int oR_len;
+    int mo_len;
+    int remaining; // result of the last sweep
+    // results of solve
+    int status;
+    int best_remaining;
+    int best_has_x;
+    long long best_loop;
+    double best_value;
+    double objective;
+    unsigned long long updates;
+    unsigned long long sweeps;
+    double alg_bytes;
+};
+
+// Per-batch lane storage (struct of arrays over lanes).
+struct DevBatch
+{
+    int n_lanes;
+    int order_cap; // entries per lane in oR / mo
+    double* P;       // [lanes][nnz]  CSC order
+    double* pi;      // [lanes][m]
+    uint32_t* x;     // [lanes][xw32]
+    uint32_t* bestx; // [lanes][xw32]
+    RC* R;           // [lanes][max_row + 2]
+    int* oR;         // [lanes][order_cap]
+    int2* mo;        // [lanes][order_cap]
+    LaneCtl* ctl;    // [lanes]
+    double* kappa;   // [lanes] input of bxg_batch_sweep
+    // scratch used when a row does not fit the shared-memory budget
+    double* g_pown;  // [lanes][max_row] or nullptr
+    int* g_opos;     // [lanes][max_row] or nullptr
+};
+
+struct LaunchCfg
+{
+    int threads;
+    size_t smem;
+    int pi_in_smem, x_in_smem, r_in_smem;
+};
+
+LaunchCfg plan_launch(const DevProblem& pb, int device);
+
+void launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+                  const uint32_t* d_seeds, const uint32_t* d_x0,
+                  const uint32_t* d_rng, int reset_solver, int init_on_device,
+                  double init_random, const double* d_cost_orig,
+                  const LaunchCfg& cfg, cudaStream_t s);
+void launch_order_init(const DevProblem& pb, const DevParams& pr,
+                       const DevBatch& b, int lane_first, int lane_count,
+                       const LaunchCfg& cfg, cudaStream_t s);
+void launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+                  int push, double obj_amp, const LaunchCfg& cfg,
+                  cudaStream_t s);
+void launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+                  const LaunchCfg& cfg, cudaStream_t s);
+void launch_objective(const DevProblem& pb, const DevParams& pr,
+                      const DevBatch& b, const LaunchCfg& cfg, cudaStream_t s);
+
+} // namespace bxg
+
+#endif

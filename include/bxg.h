@@ -1,0 +1,219 @@
+/* bxg.h -- C ABI of the B200 constraint-sweep engine (libbaryonyx_b200.so).
+ *
+ * The reference (quesnel/baryonyx v0.5.0) has no FFI: its hot path sits behind
+ * a compile-time "Solver" concept.  This header is the boundary
+ * a maintainer binds instead: plain C, opaque handles, caller-owned host
+ * buffers, int status returns (0 = ok, negative = bxg_status), no exceptions
+ * across the boundary.  One handle is used by one host thread at a time; each
+ * batch owns one CUDA stream.  Every entry point cites the reference interface
+ * it replaces (paths relative to the reference root).
+ *
+ * There is no CPU fallback: every compute call fails with BXG_E_CUDA when no
+ * CUDA device is usable.
+ */
+#ifndef BXG_H
+#define BXG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BXG_VERSION 1
+
+typedef enum bxg_status
+{
+    BXG_OK = 0,
+    BXG_E_INVALID = -1,      /* bad argument */
+    BXG_E_CUDA = -2,         /* CUDA runtime error / no device */
+    BXG_E_NO_SOLVER = -3,    /* solver_error_tag::no_solver_available, core:258-263 */
+    BXG_E_UNREALISABLE = -4, /* solver_error_tag::unrealisable_constraint */
+    BXG_E_MEMORY = -5,       /* solver_error_tag::not_enough_memory */
+    BXG_E_UNSUPPORTED = -6   /* feature of the reference outside this engine */
+} bxg_status;
+
+/* baryonyx::problem_solver_type, lib/include/baryonyx/core:542-550 */
+enum
+{
+    BXG_EQUALITIES_01 = 0,
+    BXG_EQUALITIES_101 = 1,
+    BXG_EQUALITIES_Z = 2,
+    BXG_INEQUALITIES_01 = 3,
+    BXG_INEQUALITIES_101 = 4,
+    BXG_INEQUALITIES_Z = 5
+};
+
+/* baryonyx::result_status, core:692-701 */
+enum
+{
+    BXG_STATUS_SUCCESS = 0,
+    BXG_STATUS_INTERNAL_ERROR = 1,
+    BXG_STATUS_UNINITIALIZED = 2,
+    BXG_STATUS_TIME_LIMIT_REACHED = 3,
+    BXG_STATUS_KAPPA_MAX_REACHED = 4,
+    BXG_STATUS_LIMIT_REACHED = 5,
+    BXG_STATUS_EMPTY_CONTEXT = 6
+};
+
+/* POD mirror of baryonyx::solver_parameters, core:294-462 (same field order;
+ * enum members carry the reference's integer values). */
+typedef struct bxg_params
+{
+    double time_limit;
+    double theta;
+    double delta;
+    double kappa_min;
+    double kappa_step;
+    double kappa_max;
+    double alpha;
+    double pushing_k_factor;
+    double pushing_objective_amplifier;
+    double init_policy_random;
+    double init_crossover_bastert_insertion;
+    double init_crossover_solution_selection_mean;
+    double init_crossover_solution_selection_stddev;
+    double init_mutation_variable_mean;
+    double init_mutation_variable_stddev;
+    double init_mutation_value_mean;
+    double init_mutation_value_stddev;
+    double init_kappa_improve_start;
+    double init_kappa_improve_increase;
+    double init_kappa_improve_stop;
+    double w;
+    uint32_t seed;
+    int32_t thread;
+    int64_t limit;
+    int32_t print_level;
+    int32_t pushes_limit;
+    int32_t pushing_iteration_limit;
+    int32_t init_population_size;
+    int32_t pre_order;
+    int32_t order;
+    int32_t float_type;
+    int32_t init_policy;
+    int32_t cost_norm;
+    int32_t mode;
+    int32_t preprocessor;
+    int32_t observer;
+    int32_t storage;
+    int32_t solver;
+    int32_t debug;
+} bxg_params;
+
+typedef struct bxg_problem bxg_problem;
+typedef struct bxg_batch bxg_batch;
+
+int bxg_version(void);
+/* Message of the last failing call on this thread. */
+const char* bxg_last_error(void);
+int bxg_device_count(void);
+
+/* solver_parameters defaults, core:410-461 */
+void bxg_default_params(bxg_params* p);
+/* context_set_solver_parameters, lib/src/private.cpp:51-172 (validation and
+ * clamping; w becomes a sweep count). */
+void bxg_clamp_params(const bxg_params* in, bxg_params* out);
+
+/* ---- problem -------------------------------------------------------------
+ * Replaces the Solver constructors (itm-solver-inequalities-01.cpp:72-107,
+ * -equalities-01.cpp:68-98, -inequalities-101.cpp:82-130,
+ * -equalities-101.cpp:80-113, -inequalities-Z.cpp:98-189) and
+ * sparse_matrix<int> (sparse-matrix.hpp:86-186).  Input = the merged
+ * constraints make_merged_constraints returns (merged-constraint.cpp:297-343)
+ * in CSR form: row k holds col[row_ptr[k]..row_ptr[k+1]) with integer factors
+ * and cmin[k] <= row <= cmax[k] (INT_MIN / INT_MAX for open sides); the
+ * objective as (variable, factor) pairs in file order plus its constant.
+ * Uploads the structure to `device` and builds the CSC index there. */
+int bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
+                       const int32_t* factor, const int32_t* cmin,
+                       const int32_t* cmax, int problem_type, int maximize,
+                       int n_obj, const int32_t* obj_var,
+                       const double* obj_factor, double cost_constant,
+                       int device, bxg_problem** out);
+void bxg_problem_destroy(bxg_problem* pb);
+int bxg_problem_info(const bxg_problem* pb, int* m, int* n, int* nnz,
+                     int* max_row, int* problem_type);
+/* problem::which_problem_type, lib/src/problem.hpp:72-122 */
+int bxg_which_problem_type(int nnz, const int32_t* factor, int has_inequality);
+
+/* ---- batch of lanes --------------------------------------------------------
+ * A lane is one independent Solver instance + its x, random engine and
+ * compute_order state (what one worker of the reference owns,
+ * itm-optimizer-common.hpp:620-656).  `p` must be clamped.  Allocates
+ * P[n_lanes][nnz], pi[n_lanes][m], x, R scratch on the problem's device and
+ * computes the normalised costs and delta once (normalize_costs / compute_delta,
+ * itm-common.hpp:917-998). */
+int bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p,
+                     bxg_batch** out);
+void bxg_batch_destroy(bxg_batch* b);
+int bxg_batch_info(const bxg_batch* b, int* n_lanes, double* delta,
+                   double* theta, int64_t* device_bytes);
+/* Value modelled in the slot one past the reduced-cost scratch, which the
+ * reference reads for its longest row (undefined behaviour there;
+ * itm-solver-inequalities-01.cpp:198-203).  Default 0.0. */
+int bxg_batch_set_tail_value(bxg_batch* b, double v);
+
+/* Start a run on every lane: random_engine(seed), P = pi = 0, x from the init
+ * policy followed by the Bernoulli(init_policy_random) flips, then
+ * compute_order::init (solver_functor::operator(), itm-solver-common.hpp:63-133).
+ * seeds has n_lanes entries.  reset_solver = 0 keeps P and pi (a worker of the
+ * optimizer never resets them between restarts). */
+int bxg_batch_begin(bxg_batch* b, const uint32_t* seeds, int reset_solver);
+
+/* Parity taps on one lane (any pointer may be NULL).  x_words: n/64+1 words
+ * (bit_array layout, bit-array.hpp:60-66); P is nnz values in the reference's
+ * row-major order; order_list = compute_order::R, or m_order as (k, amount)
+ * pairs for the infeasibility orders. */
+int bxg_batch_get_state(bxg_batch* b, int lane, uint64_t* x_words, double* pi,
+                        double* P, uint32_t* rng_state, int32_t* order_list,
+                        int32_t* order_len, double* norm_cost);
+/* set_x also re-runs compute_order::init for the lane. */
+int bxg_batch_set_state(bxg_batch* b, int lane, const uint64_t* x_words,
+                        const double* pi, const double* P,
+                        const uint32_t* rng_state);
+
+/* One sweep on every lane = compute_order::run (push = 0) or push_and_run
+ * (push = 1), itm-common.hpp:682-880, i.e. compute_update_row /
+ * push_and_compute_update_row over the lane's order list followed by the
+ * violated-row scan.  kappa: n_lanes host values; remaining: n_lanes host
+ * outputs (may be NULL). */
+int bxg_batch_sweep(bxg_batch* b, int push, const double* kappa,
+                    double objective_amplifier, int32_t* remaining);
+
+/* default_cost_type::results (itm-common.hpp:1140-1147) of the lanes' current x. */
+int bxg_batch_objective(bxg_batch* b, double* value);
+
+/* Whole run of solver_functor::operator() (itm-solver-common.hpp:135-225) on
+ * every lane, on the device: sweeps with the kappa schedule, then the push
+ * phase, tracking the best x.  Requires bxg_batch_begin.  Host outputs, each
+ * n_lanes long, any may be NULL: status (result_status), value, remaining
+ * constraints of the best, loop index of the best. */
+int bxg_batch_solve(bxg_batch* b, int32_t* status, double* value,
+                    int32_t* remaining, int64_t* loop);
+/* Best x of a lane as bytes (n entries 0/1), like solution::variables. */
+int bxg_batch_best(bxg_batch* b, int lane, int8_t* x);
+/* Index of the best lane (feasible first, then objective), with its value. */
+int bxg_batch_argbest(bxg_batch* b, int* lane, double* value, int* remaining);
+
+/* Work counters since batch creation: constraint updates (order-list entries
+ * processed), sweeps, and algorithmic bytes (SURVEY.md 8d formula). */
+int bxg_batch_counters(bxg_batch* b, int64_t* updates, int64_t* sweeps,
+                       double* algorithmic_bytes);
+int bxg_batch_reset_counters(bxg_batch* b);
+/* Device time of the last bxg_batch_sweep / bxg_batch_solve, CUDA events on
+ * the batch's stream, milliseconds. */
+int bxg_batch_last_ms(bxg_batch* b, float* ms);
+/* Launches issued by this batch since creation (kernels of this library). */
+int bxg_batch_launches(bxg_batch* b, int64_t* launches);
+
+/* Device-resident variant of begin+solve for benchmarking / pipelines: x0 per
+ * lane already in device memory (uint32 words, bxg_batch_words32 per lane). */
+int bxg_batch_words32(const bxg_batch* b);
+int bxg_batch_begin_device(bxg_batch* b, const uint32_t* d_x0,
+                           const uint32_t* d_rng, int reset_solver);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
