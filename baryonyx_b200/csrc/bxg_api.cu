@@ -118,10 +118,10 @@ struct bxg_batch
     double tail_value = 0;
     std::vector<double> norm_cost, powtab;
 
-    DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_pown;
+    DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_Rv;
+    DevBuf<unsigned char> d_scratch;
     DevBuf<uint32_t> d_x, d_bestx, d_seeds, d_x0, d_rng0;
-    DevBuf<RC> d_R;
-    DevBuf<int> d_oR, d_opos;
+    DevBuf<int> d_oR;
     DevBuf<int2> d_mo;
     DevBuf<LaneCtl> d_ctl;
 
@@ -551,6 +551,7 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.n_obj = n_obj;
     d.obj_any_order = pb->obj_any_order;
     d.need_z = pb->family == FAM_Z;
+    d.tail_rows = pb->tail_rows;
     d.cost_constant = cost_constant;
     d.row_ptr = pb->d_row_ptr.p;
     d.row_col = pb->d_row_col.p;
@@ -687,7 +688,7 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(b->d_pi.alloc(L * m));
     CUDA_TRY(b->d_x.alloc(L * pb->dev.xw32));
     CUDA_TRY(b->d_bestx.alloc(L * pb->dev.xw32));
-    CUDA_TRY(b->d_R.alloc(L * (pb->max_row + 2)));
+    CUDA_TRY(b->d_Rv.alloc(L * (pb->max_row + 2)));
     CUDA_TRY(b->d_oR.alloc(L * b->order_cap));
     CUDA_TRY(b->d_mo.alloc(L * b->order_cap));
     CUDA_TRY(b->d_ctl.alloc(L));
@@ -700,10 +701,8 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(cudaMemset(b->d_bestx.p, 0, b->d_bestx.bytes()));
 
     b->cfg = plan_launch(pb->dev, pb->device);
-    if (!b->cfg.r_in_smem) {
-        CUDA_TRY(b->d_pown.alloc(L * (pb->max_row + 1)));
-        CUDA_TRY(b->d_opos.alloc(L * (pb->max_row + 1)));
-    }
+    if (!b->cfg.r_in_smem)
+        CUDA_TRY(b->d_scratch.alloc(L * lane_scratch_bytes(pb->dev, b->cfg)));
 
     DevBatch& d = b->dev;
     d.n_lanes = n_lanes;
@@ -712,13 +711,12 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     d.pi = b->d_pi.p;
     d.x = b->d_x.p;
     d.bestx = b->d_bestx.p;
-    d.R = b->d_R.p;
+    d.Rv = b->d_Rv.p;
     d.oR = b->d_oR.p;
     d.mo = b->d_mo.p;
     d.ctl = b->d_ctl.p;
     d.kappa = b->d_kappa.p;
-    d.g_pown = b->d_pown.p;
-    d.g_opos = b->d_opos.p;
+    d.g_scratch = b->cfg.r_in_smem ? nullptr : b->d_scratch.p;
 
     refresh_params(b.get());
 
@@ -754,8 +752,8 @@ bxg_batch_info(const bxg_batch* b, int* n_lanes, double* delta, double* theta,
     if (device_bytes)
         *device_bytes = static_cast<int64_t>(
           b->d_P.bytes() + b->d_pi.bytes() + b->d_x.bytes() + b->d_bestx.bytes() +
-          b->d_R.bytes() + b->d_oR.bytes() + b->d_mo.bytes() + b->d_ctl.bytes() +
-          b->d_pown.bytes() + b->d_opos.bytes());
+          b->d_Rv.bytes() + b->d_oR.bytes() + b->d_mo.bytes() + b->d_ctl.bytes() +
+          b->d_scratch.bytes());
     return BXG_OK;
 }
 

@@ -97,11 +97,54 @@ uniform_below(uint32_t& s, uint32_t b)
 }
 
 // ---------------------------------------------------------------------------
-// std::shuffle, executed by ONE thread on an array view.
+// Array views for the single-thread algorithms below.  A view has an element
+// type E and get / set; Plain<T> is a pointer, Pairs keeps a key array and an
+// id array in step (the reduced-cost scratch of a row: sort key + position in
+// the row).
 // ---------------------------------------------------------------------------
 template<typename T>
+struct Plain
+{
+    using E = T;
+    T* p;
+    __device__ __forceinline__ T get(int i) const { return p[i]; }
+    __device__ __forceinline__ void set(int i, const T& v) const { p[i] = v; }
+};
+
+struct KeyId
+{
+    unsigned long long k;
+    int id;
+};
+
+struct Pairs
+{
+    using E = KeyId;
+    unsigned long long* k;
+    int* id;
+    __device__ __forceinline__ KeyId get(int i) const { return KeyId{ k[i], id[i] }; }
+    __device__ __forceinline__ void set(int i, const KeyId& v) const
+    {
+        k[i] = v.k;
+        id[i] = v.id;
+    }
+};
+
+template<typename A>
+__device__ __forceinline__ void
+seq_swap(const A& a, int i, int j)
+{
+    typename A::E t = a.get(i);
+    a.set(i, a.get(j));
+    a.set(j, t);
+}
+
+// ---------------------------------------------------------------------------
+// std::shuffle (stl_algo.h:3738-3803) on a[base .. base+n), ONE thread.
+// ---------------------------------------------------------------------------
+template<typename A>
 __device__ inline void
-seq_shuffle(T* a, int n, uint32_t& s)
+seq_shuffle(const A& a, int base, int n, uint32_t& s)
 {
     if (n <= 1)
         return;
@@ -110,24 +153,16 @@ seq_shuffle(T* a, int n, uint32_t& s)
         int i = 1;
         if ((n % 2) == 0) {
             const uint32_t j = uniform_below(s, 1u);
-            T t = a[i];
-            a[i] = a[j];
-            a[j] = t;
+            seq_swap(a, base + i, base + (int)j);
             ++i;
         }
         while (i != n) {
             const uint32_t swap_range = (uint32_t)i + 1u;
             const uint32_t b1 = swap_range + 1u;
             const uint32_t x = uniform_below(s, swap_range * b1 - 1u);
-            uint32_t j = x / b1;
-            T t = a[i];
-            a[i] = a[j];
-            a[j] = t;
+            seq_swap(a, base + i, base + (int)(x / b1));
             ++i;
-            j = x % b1;
-            t = a[i];
-            a[i] = a[j];
-            a[j] = t;
+            seq_swap(a, base + i, base + (int)(x % b1));
             ++i;
         }
         return;
@@ -135,90 +170,115 @@ seq_shuffle(T* a, int n, uint32_t& s)
 
     for (int i = 1; i != n; ++i) {
         const uint32_t j = uniform_below(s, (uint32_t)i);
-        T t = a[i];
-        a[i] = a[j];
-        a[j] = t;
+        seq_swap(a, base + i, base + (int)j);
     }
 }
 
-// ---------------------------------------------------------------------------
-// std::sort (introsort + final insertion sort), executed by ONE thread.
-// Less is a functor bool(const T&, const T&).
-// ---------------------------------------------------------------------------
-template<typename T, typename Less>
+// The engine draws of std::shuffle on n elements without moving anything
+// (the draws do not depend on the elements).
 __device__ inline void
-seq_unguarded_linear_insert(T* a, int last, Less less)
+seq_shuffle_draws(int n, uint32_t& s)
 {
-    T val = a[last];
+    if (n <= 1)
+        return;
+    if (2147483645u / (uint32_t)n >= (uint32_t)n) {
+        int i = 1;
+        if ((n % 2) == 0) {
+            uniform_below(s, 1u);
+            ++i;
+        }
+        while (i != n) {
+            const uint32_t swap_range = (uint32_t)i + 1u;
+            uniform_below(s, swap_range * (swap_range + 1u) - 1u);
+            i += 2;
+        }
+        return;
+    }
+    for (int i = 1; i != n; ++i)
+        uniform_below(s, (uint32_t)i);
+}
+
+// ---------------------------------------------------------------------------
+// std::sort (introsort + final insertion sort, stl_algo.h:1810-1957), ONE
+// thread.  Less is a functor bool(const E&, const E&).
+// ---------------------------------------------------------------------------
+template<typename A, typename Less>
+__device__ inline void
+seq_unguarded_linear_insert(const A& a, int last, Less less)
+{
+    typename A::E val = a.get(last);
     int next = last - 1;
-    while (less(val, a[next])) {
-        a[last] = a[next];
+    for (;;) {
+        typename A::E nv = a.get(next);
+        if (!less(val, nv))
+            break;
+        a.set(last, nv);
         last = next;
         --next;
     }
-    a[last] = val;
+    a.set(last, val);
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_insertion_sort(T* a, int first, int last, Less less)
+seq_insertion_sort(const A& a, int first, int last, Less less)
 {
     if (first == last)
         return;
     for (int i = first + 1; i != last; ++i) {
-        if (less(a[i], a[first])) {
-            T val = a[i];
+        typename A::E val = a.get(i);
+        if (less(val, a.get(first))) {
             for (int j = i; j > first; --j)
-                a[j] = a[j - 1];
-            a[first] = val;
+                a.set(j, a.get(j - 1));
+            a.set(first, val);
         } else
             seq_unguarded_linear_insert(a, i, less);
     }
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_push_heap(T* a, int first, int hole, int top, const T& value, Less less)
+seq_push_heap(const A& a, int first, int hole, int top, const typename A::E& value, Less less)
 {
     int parent = (hole - 1) / 2;
-    while (hole > top && less(a[first + parent], value)) {
-        a[first + hole] = a[first + parent];
+    while (hole > top && less(a.get(first + parent), value)) {
+        a.set(first + hole, a.get(first + parent));
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    a[first + hole] = value;
+    a.set(first + hole, value);
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_adjust_heap(T* a, int first, int hole, int len, const T& value, Less less)
+seq_adjust_heap(const A& a, int first, int hole, int len, const typename A::E& value, Less less)
 {
     const int top = hole;
     int second = hole;
     while (second < (len - 1) / 2) {
         second = 2 * (second + 1);
-        if (less(a[first + second], a[first + (second - 1)]))
+        if (less(a.get(first + second), a.get(first + (second - 1))))
             second--;
-        a[first + hole] = a[first + second];
+        a.set(first + hole, a.get(first + second));
         hole = second;
     }
     if ((len & 1) == 0 && second == (len - 2) / 2) {
         second = 2 * (second + 1);
-        a[first + hole] = a[first + (second - 1)];
+        a.set(first + hole, a.get(first + (second - 1)));
         hole = second - 1;
     }
     seq_push_heap(a, first, hole, top, value, less);
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_heap_sort(T* a, int first, int last, Less less)
+seq_heap_sort(const A& a, int first, int last, Less less)
 {
     const int len = last - first;
     if (len >= 2) {
         int parent = (len - 2) / 2;
         for (;;) {
-            T value = a[first + parent];
+            typename A::E value = a.get(first + parent);
             seq_adjust_heap(a, first, parent, len, value, less);
             if (parent == 0)
                 break;
@@ -227,59 +287,64 @@ seq_heap_sort(T* a, int first, int last, Less less)
     }
     while (last - first > 1) {
         --last;
-        T value = a[last];
-        a[last] = a[first];
+        typename A::E value = a.get(last);
+        a.set(last, a.get(first));
         seq_adjust_heap(a, first, 0, last - first, value, less);
     }
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_move_median_to_first(T* a, int result, int ia, int ib, int ic, Less less)
+seq_move_median_to_first(const A& a, int result, int ia, int ib, int ic, Less less)
 {
+    const typename A::E va = a.get(ia), vb = a.get(ib), vc = a.get(ic);
     int pick;
-    if (less(a[ia], a[ib])) {
-        if (less(a[ib], a[ic]))
+    if (less(va, vb)) {
+        if (less(vb, vc))
             pick = ib;
-        else if (less(a[ia], a[ic]))
+        else if (less(va, vc))
             pick = ic;
         else
             pick = ia;
-    } else if (less(a[ia], a[ic]))
+    } else if (less(va, vc))
         pick = ia;
-    else if (less(a[ib], a[ic]))
+    else if (less(vb, vc))
         pick = ic;
     else
         pick = ib;
-    T t = a[result];
-    a[result] = a[pick];
-    a[pick] = t;
+    seq_swap(a, result, pick);
 }
 
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline int
-seq_unguarded_partition(T* a, int first, int last, int pivot, Less less)
+seq_unguarded_partition(const A& a, int first, int last, int pivot, Less less)
 {
+    const typename A::E pv = a.get(pivot); // the pivot slot is outside [first, last)
     for (;;) {
-        while (less(a[first], a[pivot]))
+        typename A::E fv = a.get(first);
+        while (less(fv, pv)) {
             ++first;
+            fv = a.get(first);
+        }
         --last;
-        while (less(a[pivot], a[last]))
+        typename A::E lv = a.get(last);
+        while (less(pv, lv)) {
             --last;
+            lv = a.get(last);
+        }
         if (!(first < last))
             return first;
-        T t = a[first];
-        a[first] = a[last];
-        a[last] = t;
+        a.set(first, lv);
+        a.set(last, fv);
         ++first;
     }
 }
 
 // Explicit stack instead of recursion: the reference recurses on the right
 // part and loops on the left; sub-ranges are disjoint, so order is free.
-template<typename T, typename Less>
+template<typename A, typename Less>
 __device__ inline void
-seq_std_sort(T* a, int n, Less less)
+seq_std_sort(const A& a, int n, Less less)
 {
     if (n <= 1)
         return;

@@ -36,6 +36,8 @@ struct Shared
     int list_len;
     int order_state;
     int tmp_i;
+    int slow; // the current row takes the single-thread path
+    int n_pre;
     double d;
     double tmp_d;
     double red[32];
@@ -49,7 +51,11 @@ struct Lane
     double* P;
     double* pi;
     uint32_t* x;
-    RC* R;
+    // reduced-cost scratch of the current row
+    unsigned long long* key0; // [max_row]   sort keys in row order
+    unsigned long long* sk;   // [sort_cap]  keys being sorted
+    int* sid;                 // [sort_cap]  position in the row, moved with sk
+    double* Rv;               // [max_row+2] value left at each slot of the reference's R
     double* pown;
     int* opos;
     int* viol;
@@ -57,6 +63,7 @@ struct Lane
     int2* mo;
     LaneCtl* ctl;
     Shared* sh;
+    int sort_cap; // the CTA-wide sort handles rows up to this length
     unsigned long long updates;
     unsigned long long sweeps;
     double alg_bytes;
@@ -68,70 +75,74 @@ xbit(const uint32_t* x, int i)
     return (int)((x[i >> 5] >> (i & 31)) & 1u);
 }
 
-struct LessMin
+// ---- sort keys ------------------------------------------------------------
+// The reduced costs of a row are ordered through 64-bit integer keys: the
+// usual order-preserving map of a double (sign bit flipped for positives, all
+// bits flipped for negatives), complemented when the objective is maximised
+// so that ascending keys always give the reference's order
+// (calculator_sort, itm-common.hpp:134-148).  Rows holding a NaN or a -0.0
+// keep the raw bits instead and are compared as doubles by one thread
+// ("raw" mode): there the reference's comparator is not a total order and
+// only its own algorithm defines the result.
+__device__ __forceinline__ unsigned long long
+key_of(double v, bool maximize)
 {
-    __device__ bool operator()(const RC& a, const RC& b) const
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return maximize ? ~b : b;
+}
+
+__device__ __forceinline__ double
+value_of_key(unsigned long long k, bool maximize)
+{
+    if (maximize)
+        k = ~k;
+    k = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)k);
+}
+
+struct LessKey
+{
+    __device__ bool operator()(const KeyId& a, const KeyId& b) const { return a.k < b.k; }
+};
+
+struct LessRawMin
+{
+    __device__ bool operator()(const KeyId& a, const KeyId& b) const
     {
-        return a.value < b.value;
+        return __longlong_as_double((long long)a.k) < __longlong_as_double((long long)b.k);
     }
 };
 
-struct LessMax
+struct LessRawMax
 {
-    __device__ bool operator()(const RC& a, const RC& b) const
+    __device__ bool operator()(const KeyId& a, const KeyId& b) const
     {
-        return b.value < a.value;
+        return __longlong_as_double((long long)b.k) < __longlong_as_double((long long)a.k);
     }
 };
 
 struct PairLessDecr
 {
-    __device__ bool operator()(const int2& a, const int2& b) const
-    {
-        return b.y < a.y;
-    }
+    __device__ bool operator()(const int2& a, const int2& b) const { return b.y < a.y; }
 };
 
 struct PairLessIncr
 {
-    __device__ bool operator()(const int2& a, const int2& b) const
-    {
-        return a.y < b.y;
-    }
+    __device__ bool operator()(const int2& a, const int2& b) const { return a.y < b.y; }
 };
 
 struct PiLessDecr
 {
     const double* pi;
-    __device__ bool operator()(const int& a, const int& b) const
-    {
-        return pi[b] < pi[a];
-    }
+    __device__ bool operator()(const int& a, const int& b) const { return pi[b] < pi[a]; }
 };
 
 struct PiLessIncr
 {
     const double* pi;
-    __device__ bool operator()(const int& a, const int& b) const
-    {
-        return pi[a] < pi[b];
-    }
+    __device__ bool operator()(const int& a, const int& b) const { return pi[a] < pi[b]; }
 };
-
-// random_shuffle_unique (itm-common.hpp:117-132), one thread.
-__device__ void
-seq_shuffle_unique(RC* R, int n, uint32_t& rng)
-{
-    int ret = 0;
-    int i = 1;
-    for (; i != n; ++i) {
-        if (R[ret].value != R[i].value) {
-            seq_shuffle(R + ret, i - ret, rng);
-            ret = i;
-        }
-    }
-    seq_shuffle(R + ret, i - ret, rng);
-}
 
 // stop_iterating with the engine (itm-common.hpp:150-163)
 __device__ __forceinline__ bool
@@ -142,31 +153,139 @@ stop_iterating_rng(double value, bool maximize, uint32_t& rng)
     return maximize ? value < 0 : value > 0;
 }
 
-// select_variables of the 01 / 101 solvers (itm-solver-inequalities-01.cpp:
-// 193-206, -equalities-01.cpp:173-182, -inequalities-101.cpp:235-248,
-// -equalities-101.cpp:197-206), one thread.
-__device__ int
-select_variables_01_101(const RC* R, int r_size, int c_size, int bkmin,
-                        int bkmax, int family, bool maximize, uint32_t& rng)
+// Bounds of the scan of select_variables (itm-solver-inequalities-01.cpp:
+// 193-206, -101.cpp:235-248) for an inequality row.
+__device__ __forceinline__ void
+select_window(int family, int r_size, int c_size, int bkmin, int bkmax, int& lo, int& hi)
 {
+    if (family == FAM_01) {
+        lo = bkmin < r_size ? bkmin : r_size;
+        hi = bkmax < r_size ? bkmax : r_size;
+    } else {
+        lo = bkmin + c_size;
+        hi = (bkmax + c_size) < r_size ? (bkmax + c_size) : r_size;
+    }
+}
+
+// Scalar part of affect (itm-common.hpp:382-467): pi_k and the preference
+// step d from the values around the selection boundary.  One thread.
+__device__ __forceinline__ void
+affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0, double vsel,
+               double vnext)
+{
+    const double old_pi = L.pi[k];
+    const double kk = __ddiv_rn(kappa, __dsub_rn(1.0, kappa));
+    double d = L.pr->delta;
+    if (selected < 0) {
+        d = __dadd_rn(d, __dmul_rn(kk, __ddiv_rn(v0, 2.0)));
+    } else if (selected + 1 >= r_size) {
+        d = __dadd_rn(d, __dmul_rn(kk, __dmul_rn(vsel, 1.5)));
+    } else {
+        const double npi = __dadd_rn(old_pi, __ddiv_rn(__dadd_rn(vsel, vnext), 2.0));
+        L.pi[k] = npi;
+        d = __dadd_rn(d, __dmul_rn(kk, __dsub_rn(vnext, vsel)));
+        if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
+            L.sh->pi_changed = 1;
+    }
+    L.sh->selected = selected;
+    L.sh->d = d;
+}
+
+// Single-thread statement of calculator_sort + select_variables on the row:
+// the exact libstdc++ sort and shuffle permutations.  Used when the parallel
+// path cannot decide the row (ties across the selection boundary, NaN, -0.0).
+template<typename Less>
+__device__ void
+row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
+{
+    const DevProblem& pb = *L.pb;
+    const bool maximize = pb.maximize != 0;
+    uint32_t rng = L.sh->rng;
+    Pairs a{ L.sk, L.sid };
+
+    for (int i = 0; i != r_size; ++i) {
+        L.sk[i] = L.key0[i];
+        L.sid[i] = i;
+    }
+
+    auto value_at = [&](int p) {
+        return raw ? __longlong_as_double((long long)L.sk[p]) : value_of_key(L.sk[p], maximize);
+    };
+
+    if (r_size > 1) {
+        seq_std_sort(a, r_size, less);
+        // random_shuffle_unique, itm-common.hpp:117-132
+        int ret = 0;
+        int i = 1;
+        for (; i != r_size; ++i) {
+            const bool differ = raw ? (value_at(ret) != value_at(i)) : (L.sk[ret] != L.sk[i]);
+            if (differ) {
+                seq_shuffle(a, ret, i - ret, rng);
+                ret = i;
+            }
+        }
+        seq_shuffle(a, ret, i - ret, rng);
+    }
+
+    const int c_size = pb.family == FAM_101 ? pb.row_neg[k] : 0;
+    const int bkmin = pb.bmin[k], bkmax = pb.bmax[k];
+    int selected;
     if (bkmin == bkmax) {
         const int b = bkmin + c_size;
-        return (b < r_size ? b : r_size) - 1;
-    }
-
-    if (family == FAM_01) {
-        bkmin = bkmin < r_size ? bkmin : r_size;
-        bkmax = bkmax < r_size ? bkmax : r_size;
+        selected = (b < r_size ? b : r_size) - 1;
     } else {
-        bkmin += c_size;
-        bkmax = (bkmax + c_size) < r_size ? (bkmax + c_size) : r_size;
+        int lo, hi;
+        select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+        selected = hi - 1;
+        for (int i = lo; i <= hi; ++i) {
+            const double v = i < r_size ? value_at(i) : L.Rv[r_size];
+            if (stop_iterating_rng(v, maximize, rng)) {
+                selected = i - 1;
+                break;
+            }
+        }
     }
 
-    for (int i = bkmin; i <= bkmax; ++i)
-        if (stop_iterating_rng(R[i].value, maximize, rng))
-            return i - 1;
+    L.sh->rng = rng;
+    const double v0 = value_at(0);
+    const double vsel = selected >= 0 ? value_at(selected) : 0.0;
+    const double vnext = (selected >= 0 && selected + 1 < r_size) ? value_at(selected + 1) : 0.0;
+    affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
+}
 
-    return bkmax - 1;
+// Bitonic sort of sk[0..n2) (ascending) carrying sid, by the whole CTA.  n2
+// is a power of two.  Strides below 64 stay inside the 64 elements one warp
+// owns, so only the wide strides need a CTA barrier.
+__device__ void
+cta_bitonic_sort(unsigned long long* sk, int* sid, int n2)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int half = n2 >> 1;
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < half; t += T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const unsigned long long a = sk[i], b = sk[l];
+                const bool up = (i & kk) == 0;
+                if ((a > b) == up && a != b) {
+                    sk[i] = b;
+                    sk[l] = a;
+                    const int ia = sid[i];
+                    sid[i] = sid[l];
+                    sid[l] = ia;
+                }
+            }
+            // the next stage works with stride j/2, or kk when the next merge
+            // size starts
+            const int nj = j > 1 ? (j >> 1) : kk;
+            if (j > 32 || nj > 32)
+                __syncthreads();
+            else
+                __syncwarp();
+        }
+    }
+    __syncthreads();
 }
 
 // One constraint update (the loop body of compute_update_row /
@@ -181,8 +300,17 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
     const int r_size = pb.row_ptr[k + 1] - r0;
     const double theta = pr.theta;
     const double* __restrict__ cost = pr.cost;
+    const bool maximize = pb.maximize != 0;
+
+    if (tid == 0) {
+        L.sh->slow = 0;
+        L.alg_bytes += pb.row_bytes[k];
+    }
+    __syncthreads();
 
     // ---- A: theta decay + reduced costs (compute_reduced_costs) ----------
+    int odd = 0;   // NaN or -0.0 seen by this thread
+    int n_pre = 0; // values that neither stop the scan nor are zero
     for (int i = tid; i < r_size; i += T) {
         const int e = r0 + i;
         const int j = pb.row_col[e];
@@ -190,7 +318,6 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
         double pown = 0.0;
         int opos = c0;
         double val;
-        int f = 1;
 
         if (pb.family == FAM_01) {
             double sum_pi = 0.0, sum_p = 0.0;
@@ -208,7 +335,7 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
             val = __dsub_rn(__dsub_rn(cost[j], sum_pi), sum_p);
             if (push)
                 val = __dadd_rn(val, __dmul_rn(obj_amp, cost[i]));
-        } else if (pb.family == FAM_101) {
+        } else {
             double sum_pi = 0.0, sum_p = 0.0;
             for (int t = c0; t < c1; ++t) {
                 const int rw = pb.csc_row[t];
@@ -223,80 +350,227 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
                 sum_p = __dadd_rn(sum_p, __dmul_rn(a, p));
             }
             val = __dsub_rn(__dsub_rn(cost[j], sum_pi), sum_p);
-            f = pb.row_a[e];
-            if (f < 0)
+            if (pb.row_a[e] < 0)
                 val = -val;
             if (push)
                 val = __dadd_rn(val, __dmul_rn(obj_amp, cost[j]));
-        } else {
-            double sum = 0.0;
-            for (int t = c0; t < c1; ++t) {
-                const int rw = pb.csc_row[t];
-                const double a = fabs((double)pb.csc_a[t]);
-                double p = L.P[t];
-                if (rw == k) {
-                    p = __dmul_rn(p, theta);
-                    pown = p;
-                    opos = t;
-                }
-                sum = __dadd_rn(sum, __dmul_rn(a, __dadd_rn(L.pi[rw], p)));
-            }
-            val = __dsub_rn(cost[j], sum);
-            f = pb.row_a[e];
-            if (push)
-                val = __dadd_rn(val, __dmul_rn(obj_amp, cost[j]));
         }
 
-        RC rc;
-        rc.value = val;
-        rc.id = i;
-        rc.f = f;
-        L.R[i] = rc;
+        if (val != val || (val == 0.0 && __double_as_longlong(val) < 0))
+            odd = 1;
+        if (val != 0.0 && !(maximize ? val < 0 : val > 0))
+            ++n_pre;
+        // raw bits here; rewritten as keys below once the mode is known
+        L.key0[i] = (unsigned long long)__double_as_longlong(val);
         L.pown[i] = pown;
         L.opos[i] = opos;
     }
-    __syncthreads();
+    const bool raw = __syncthreads_or(odd) != 0;
 
-    // ---- B: calculator_sort + select_variables + scalar part of affect ---
-    if (tid == 0) {
-        uint32_t rng = L.sh->rng;
-        const bool maximize = pb.maximize != 0;
+    int n2 = 2;
+    while (n2 < r_size)
+        n2 <<= 1;
 
-        if (r_size > 1) {
-            if (maximize)
-                seq_std_sort(L.R, r_size, LessMax());
-            else
-                seq_std_sort(L.R, r_size, LessMin());
-            seq_shuffle_unique(L.R, r_size, rng);
+    if (raw || r_size < 2 || n2 > L.sort_cap) {
+        if (!raw)
+            for (int i = tid; i < r_size; i += T)
+                L.key0[i] = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
+        __syncthreads();
+        if (tid == 0)
+            L.sh->slow = 1;
+    } else {
+        // ---- B: parallel order + selection ---------------------------------
+        for (int i = tid; i < n2; i += T) {
+            unsigned long long key = ~0ull;
+            if (i < r_size) {
+                key = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
+                L.key0[i] = key;
+            }
+            L.sk[i] = key;
+            L.sid[i] = i;
         }
+        // block count of n_pre
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            n_pre += __shfl_xor_sync(0xffffffffu, n_pre, o);
+        if ((tid & 31) == 0)
+            L.sh->redi[tid >> 5] = n_pre;
+        __syncthreads();
+        cta_bitonic_sort(L.sk, L.sid, n2);
 
-        const int c_size = pb.family == FAM_101 ? pb.row_neg[k] : 0;
-        L.alg_bytes += pb.row_bytes[k];
-        const int selected = select_variables_01_101(
-          L.R, r_size, c_size, pb.bmin[k], pb.bmax[k], pb.family, maximize, rng);
+        // equal keys next to each other = a run random_shuffle_unique shuffles
+        int tie = 0;
+        for (int p = tid + 1; p < r_size; p += T)
+            tie |= (L.sk[p] == L.sk[p - 1]);
+        const bool has_tie = __syncthreads_or(tie) != 0;
+        const uint32_t rng0 = L.sh->rng;
+        int total_draws = 0;
+        int reject = 0;
 
-        // affect, itm-common.hpp:382-467
-        const double old_pi = L.pi[k];
-        const double kk = __ddiv_rn(kappa, __dsub_rn(1.0, kappa));
-        double d = pr.delta;
-        if (selected < 0) {
-            d = __dadd_rn(d, __dmul_rn(kk, __ddiv_rn(L.R[0].value, 2.0)));
-        } else if (selected + 1 >= r_size) {
-            d = __dadd_rn(d, __dmul_rn(kk, __dmul_rn(L.R[selected].value, 1.5)));
-        } else {
-            const double lo = L.R[selected].value, hi = L.R[selected + 1].value;
-            const double npi = __dadd_rn(old_pi, __ddiv_rn(__dadd_rn(lo, hi), 2.0));
-            L.pi[k] = npi;
-            d = __dadd_rn(d, __dmul_rn(kk, __dsub_rn(hi, lo)));
-            if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
-                L.sh->pi_changed = 1;
+        if (has_tie) {
+            // Draws of all the std::shuffle calls, in sorted order.  A run of
+            // n equal keys starting at a draws floor(n/2) numbers: the element
+            // at odd offset o owns draw number (o-1)/2 (n odd) or o/2 (n even,
+            // where offset 1 owns the single-swap draw).  Its index in the
+            // row's draw sequence is the count of odd offsets before it.
+            const int C = (r_size + T - 1) / T;
+            const int p0 = min(r_size, tid * C), p1 = min(r_size, p0 + C);
+            int local = 0;
+            for (int p = p0; p < p1; ++p) {
+                const unsigned long long key = L.sk[p];
+                if (p > 0 && L.sk[p - 1] == key) {
+                    int lo = 0, hi = p; // first index holding key
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (L.sk[mid] < key)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    local += (p - lo) & 1;
+                }
+            }
+            // exclusive scan of `local` over the threads
+            int incl = local;
+            const int ln = tid & 31, wp = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (ln >= o)
+                    incl += v;
+            }
+            if (ln == 31)
+                L.sh->red[wp] = (double)incl;
+            __syncthreads();
+            int before = 0;
+            const int nw = T >> 5;
+            for (int w = 0; w < nw; ++w) {
+                const int v = (int)L.sh->red[w];
+                if (w < wp)
+                    before += v;
+                total_draws += v;
+            }
+            int t = before + incl - local;
+
+            for (int p = p0; p < p1; ++p) {
+                const unsigned long long key = L.sk[p];
+                const bool eq_prev = p > 0 && L.sk[p - 1] == key;
+                const bool eq_next = p + 1 < r_size && L.sk[p + 1] == key;
+                if (!eq_prev && !eq_next)
+                    continue;
+                int lo = 0, hi = p;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (L.sk[mid] < key)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                const int a = lo;
+                lo = p;
+                hi = r_size; // first index above key
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (L.sk[mid] <= key)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                const int n = lo - a;
+                const int o = p - a;
+                uint32_t uerange = 0;
+                if (n & 1) {
+                    if (o & 1)
+                        uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
+                } else if (o == 1)
+                    uerange = 2u;
+                else if (o >= 2 && !(o & 1))
+                    uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
+                if (uerange) {
+                    // this draw is number t' = (count of odd offsets before p)
+                    // for o odd that is t; for o even (n even, o >= 2) the
+                    // odd offset o-1 < p is already counted in t as well
+                    const uint32_t g = lcg_mul(rng0, lcg_pow((uint64_t)t + 1u));
+                    const uint32_t scaling = 2147483645u / uerange;
+                    if (g - 1u >= uerange * scaling)
+                        reject = 1;
+                }
+                t += o & 1;
+            }
         }
+        const bool any_reject = has_tie && __syncthreads_or(reject) != 0;
 
-        L.sh->rng = rng;
-        L.sh->selected = selected;
-        L.sh->d = d;
+        if (tid == 0) {
+            uint32_t rng = rng0;
+            if (any_reject) {
+                // a uniform draw was rejected somewhere: replay the draws
+                int ret = 0;
+                int i = 1;
+                for (; i != r_size; ++i) {
+                    if (L.sk[ret] != L.sk[i]) {
+                        seq_shuffle_draws(i - ret, rng);
+                        ret = i;
+                    }
+                }
+                seq_shuffle_draws(i - ret, rng);
+            } else if (total_draws)
+                rng = lcg_mul(rng0, lcg_pow((uint64_t)total_draws));
+
+            int npre = 0;
+            const int nw = T >> 5;
+            for (int w = 0; w < nw; ++w)
+                npre += L.sh->redi[w];
+
+            const int c_size = pb.family == FAM_101 ? pb.row_neg[k] : 0;
+            const int bkmin = pb.bmin[k], bkmax = pb.bmax[k];
+            int selected;
+            if (bkmin == bkmax) {
+                const int b = bkmin + c_size;
+                selected = (b < r_size ? b : r_size) - 1;
+            } else {
+                int lo, hi;
+                select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+                selected = hi - 1;
+                // the first npre sorted values neither stop nor draw
+                int i = lo;
+                if (i < npre)
+                    i = npre;
+                for (; i <= hi; ++i) {
+                    const double v = i < r_size ? value_of_key(L.sk[i], maximize) : L.Rv[r_size];
+                    if (stop_iterating_rng(v, maximize, rng)) {
+                        selected = i - 1;
+                        break;
+                    }
+                }
+            }
+
+            if (selected >= 0 && selected + 1 < r_size && L.sk[selected] == L.sk[selected + 1]) {
+                // equal values on both sides of the boundary: which of them
+                // are selected is decided by the exact permutations
+                L.sh->slow = 1;
+            } else {
+                L.sh->rng = rng;
+                const double v0 = value_of_key(L.sk[0], maximize);
+                const double vsel = selected >= 0 ? value_of_key(L.sk[selected], maximize) : 0.0;
+                const double vnext =
+                  (selected >= 0 && selected + 1 < r_size) ? value_of_key(L.sk[selected + 1], maximize) : 0.0;
+                affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
+            }
+        }
     }
     __syncthreads();
+
+    if (L.sh->slow) {
+        if (tid == 0) {
+            if (!raw)
+                row_select_exact(L, k, r_size, kappa, false, LessKey());
+            else if (maximize)
+                row_select_exact(L, k, r_size, kappa, true, LessRawMax());
+            else
+                row_select_exact(L, k, r_size, kappa, true, LessRawMin());
+        }
+        __syncthreads();
+    }
 
     // ---- D: x / P part of affect ------------------------------------------
     {
@@ -304,18 +578,22 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
         const double d = L.sh->d;
         const bool all_out = selected < 0;
         const bool all_in = !all_out && (selected + 1 >= r_size);
+        const bool keep_tail = pb.tail_rows != 0;
 
         for (int p = tid; p < r_size; p += T) {
-            const RC rc = L.R[p];
+            const int id = L.sid[p];
             const bool in = all_in || (!all_out && p <= selected);
-            const bool set = in != (rc.f < 0);
-            const int j = pb.row_col[r0 + rc.id];
-            const double pv = L.pown[rc.id];
-            L.P[L.opos[rc.id]] = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
+            const bool neg = pb.family != FAM_01 && pb.row_a[r0 + id] < 0;
+            const bool set = in != neg;
+            const int j = pb.row_col[r0 + id];
+            const double pv = L.pown[id];
+            L.P[L.opos[id]] = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
             if (set)
                 atomicOr(&L.x[j >> 5], 1u << (j & 31));
             else
                 atomicAnd(&L.x[j >> 5], ~(1u << (j & 31)));
+            if (keep_tail)
+                L.Rv[p] = raw ? __longlong_as_double((long long)L.sk[p]) : value_of_key(L.sk[p], maximize);
         }
     }
     __syncthreads();
@@ -434,7 +712,7 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     case ORDER_RANDOM_SORTING:
         if (tid == 0) {
             uint32_t rng = L.sh->rng;
-            seq_shuffle(L.oR, ls.oR_len, rng);
+            seq_shuffle(Plain<int>{ L.oR }, 0, ls.oR_len, rng);
             L.sh->rng = rng;
         }
         __syncthreads();
@@ -448,9 +726,9 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     case ORDER_INFEASIBILITY_INCR:
         if (tid == 0) {
             if (order == ORDER_INFEASIBILITY_DECR)
-                seq_std_sort(L.mo, ls.mo_len, PairLessDecr());
+                seq_std_sort(Plain<int2>{ L.mo }, ls.mo_len, PairLessDecr());
             else
-                seq_std_sort(L.mo, ls.mo_len, PairLessIncr());
+                seq_std_sort(Plain<int2>{ L.mo }, ls.mo_len, PairLessIncr());
         }
         __syncthreads();
         L.updates += ls.mo_len;
@@ -463,9 +741,9 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     case ORDER_LAGRANGIAN_INCR:
         if (tid == 0) {
             if (order == ORDER_LAGRANGIAN_DECR)
-                seq_std_sort(L.oR, ls.oR_len, PiLessDecr{ L.pi });
+                seq_std_sort(Plain<int>{ L.oR }, ls.oR_len, PiLessDecr{ L.pi });
             else
-                seq_std_sort(L.oR, ls.oR_len, PiLessIncr{ L.pi });
+                seq_std_sort(Plain<int>{ L.oR }, ls.oR_len, PiLessIncr{ L.pi });
         }
         __syncthreads();
         L.updates += ls.oR_len;
@@ -477,7 +755,7 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     case ORDER_PI_SIGN_CHANGE: {
         if (tid == 0) {
             uint32_t rng = L.sh->rng;
-            seq_shuffle(L.oR, ls.oR_len, rng);
+            seq_shuffle(Plain<int>{ L.oR }, 0, ls.oR_len, rng);
             L.sh->rng = rng;
             L.sh->pi_changed = 0;
         }
@@ -548,7 +826,22 @@ objective(Lane& L)
 struct SmemPlan
 {
     int pi_in_smem, x_in_smem, r_in_smem;
+    int sort_cap;
 };
+
+// Bytes of the per-lane row scratch (key0, sk, sid, pown, opos), laid out the
+// same way in shared memory or in the batch's global scratch.
+__host__ __device__ inline size_t
+row_scratch_bytes(int max_row, int sort_cap)
+{
+    size_t n = 0;
+    n += sizeof(unsigned long long) * (size_t)max_row;  // key0
+    n += sizeof(unsigned long long) * (size_t)sort_cap; // sk
+    n += sizeof(double) * (size_t)(max_row + 1);        // pown
+    n += sizeof(int) * (size_t)sort_cap;                // sid
+    n += sizeof(int) * (size_t)(max_row + 1);           // opos
+    return (n + 15) & ~size_t(15);
+}
 
 __device__ void
 lane_open(Lane& L, Lists& ls, const DevProblem& pb, const DevParams& pr,
@@ -566,22 +859,38 @@ lane_open(Lane& L, Lists& ls, const DevProblem& pb, const DevParams& pr,
     L.ctl = b.ctl + lane_id;
     L.oR = b.oR + (size_t)lane_id * b.order_cap;
     L.mo = b.mo + (size_t)lane_id * b.order_cap;
+    L.sort_cap = plan.r_in_smem ? plan.sort_cap : 0;
 
     double* g_pi = b.pi + (size_t)lane_id * pb.m;
     uint32_t* g_x = b.x + (size_t)lane_id * pb.xw32;
-    RC* g_R = b.R + (size_t)lane_id * (pb.max_row + 2);
+    double* g_Rv = b.Rv + (size_t)lane_id * (pb.max_row + 2);
+
+    {
+        unsigned char* base;
+        if (plan.r_in_smem) {
+            base = smem + off;
+            off += row_scratch_bytes(pb.max_row, plan.sort_cap);
+        } else
+            base = b.g_scratch + (size_t)lane_id * row_scratch_bytes(pb.max_row, plan.sort_cap);
+        size_t o = 0;
+        L.key0 = reinterpret_cast<unsigned long long*>(base + o);
+        o += sizeof(unsigned long long) * (size_t)pb.max_row;
+        L.sk = reinterpret_cast<unsigned long long*>(base + o);
+        o += sizeof(unsigned long long) * (size_t)plan.sort_cap;
+        L.pown = reinterpret_cast<double*>(base + o);
+        o += sizeof(double) * (size_t)(pb.max_row + 1);
+        L.sid = reinterpret_cast<int*>(base + o);
+        o += sizeof(int) * (size_t)plan.sort_cap;
+        L.opos = reinterpret_cast<int*>(base + o);
+    }
 
     if (plan.r_in_smem) {
-        L.R = reinterpret_cast<RC*>(smem + off);
-        off += sizeof(RC) * (size_t)(pb.max_row + 2);
-        L.pown = reinterpret_cast<double*>(smem + off);
-        off += sizeof(double) * (size_t)(pb.max_row + 1);
+        L.Rv = reinterpret_cast<double*>(smem + off);
+        off += sizeof(double) * (size_t)(pb.max_row + 2);
         for (int i = tid; i < pb.max_row + 2; i += T)
-            L.R[i] = g_R[i];
-    } else {
-        L.R = g_R;
-        L.pown = b.g_pown + (size_t)lane_id * (pb.max_row + 1);
-    }
+            L.Rv[i] = g_Rv[i];
+    } else
+        L.Rv = g_Rv;
 
     if (plan.pi_in_smem) {
         L.pi = reinterpret_cast<double*>(smem + off);
@@ -590,12 +899,6 @@ lane_open(Lane& L, Lists& ls, const DevProblem& pb, const DevParams& pr,
             L.pi[i] = g_pi[i];
     } else
         L.pi = g_pi;
-
-    if (plan.r_in_smem) {
-        L.opos = reinterpret_cast<int*>(smem + off);
-        off += sizeof(int) * (size_t)(pb.max_row + 1);
-    } else
-        L.opos = b.g_opos + (size_t)lane_id * (pb.max_row + 1);
 
     L.viol = reinterpret_cast<int*>(smem + off);
     off += sizeof(int) * (size_t)pb.m;
@@ -630,9 +933,9 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
     __syncthreads();
 
     if (plan.r_in_smem) {
-        RC* g_R = b.R + (size_t)lane_id * (pb.max_row + 2);
+        double* g_Rv = b.Rv + (size_t)lane_id * (pb.max_row + 2);
         for (int i = tid; i < pb.max_row + 2; i += T)
-            g_R[i] = L.R[i];
+            g_Rv[i] = L.Rv[i];
     }
     if (plan.pi_in_smem) {
         double* g_pi = b.pi + (size_t)lane_id * pb.m;
@@ -675,7 +978,7 @@ k_begin(DevProblem pb, DevParams pr, DevBatch b, const uint32_t* seeds,
 
     double* g_pi = b.pi + (size_t)lane_id * pb.m;
     uint32_t* g_x = b.x + (size_t)lane_id * pb.xw32;
-    RC* g_R = b.R + (size_t)lane_id * (pb.max_row + 2);
+    double* g_Rv = b.Rv + (size_t)lane_id * (pb.max_row + 2);
     double* g_P = b.P + (size_t)lane_id * pb.nnz;
     LaneCtl* ctl = b.ctl + lane_id;
 
@@ -684,13 +987,8 @@ k_begin(DevProblem pb, DevParams pr, DevBatch b, const uint32_t* seeds,
             g_P[i] = 0.0;
         for (int i = tid; i < pb.m; i += T)
             g_pi[i] = 0.0;
-        for (int i = tid; i < pb.max_row + 2; i += T) {
-            RC rc;
-            rc.value = (i == pb.max_row) ? pr.tail_value : 0.0;
-            rc.id = 0;
-            rc.f = 0;
-            g_R[i] = rc;
-        }
+        for (int i = tid; i < pb.max_row + 2; i += T)
+            g_Rv[i] = (i == pb.max_row) ? pr.tail_value : 0.0;
     }
 
     uint32_t rng;
@@ -931,22 +1229,35 @@ k_solve(DevProblem pb, DevParams pr, DevBatch b, SmemPlan plan)
 // ---------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------
+static int
+pow2_at_least(int v)
+{
+    int p = 2;
+    while (p < v)
+        p <<= 1;
+    return p;
+}
+
 static size_t
-smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in)
+smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap)
 {
     size_t off = (sizeof(Shared) + 15) & ~size_t(15);
     if (r_in) {
-        off += sizeof(RC) * (size_t)(pb.max_row + 2);
-        off += sizeof(double) * (size_t)(pb.max_row + 1);
+        off += row_scratch_bytes(pb.max_row, sort_cap);
+        off += sizeof(double) * (size_t)(pb.max_row + 2);
     }
     if (pi_in)
         off += sizeof(double) * (size_t)pb.m;
-    if (r_in)
-        off += sizeof(int) * (size_t)(pb.max_row + 1);
     off += sizeof(int) * (size_t)pb.m;
     if (x_in)
         off += sizeof(uint32_t) * (size_t)pb.xw32;
     return off + 16;
+}
+
+size_t
+lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg)
+{
+    return row_scratch_bytes(pb.max_row, cfg.sort_cap);
 }
 
 LaunchCfg
@@ -962,14 +1273,22 @@ plan_launch(const DevProblem& pb, int device)
     cfg.r_in_smem = 1;
     cfg.pi_in_smem = 1;
     cfg.x_in_smem = 1;
+    cfg.sort_cap = pow2_at_least(pb.max_row);
     // drop the largest consumers first until the plan fits
-    if (smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem) > budget)
+    auto fits = [&]() {
+        return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap) <= budget;
+    };
+    if (!fits())
         cfg.x_in_smem = 0;
-    if (smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem) > budget)
+    if (!fits()) {
+        // rows too long for the shared-memory sort: scratch in global memory,
+        // single-thread ordering only
         cfg.r_in_smem = 0;
-    if (smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem) > budget)
+        cfg.sort_cap = pb.max_row;
+    }
+    if (!fits())
         cfg.pi_in_smem = 0;
-    cfg.smem = smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem);
+    cfg.smem = smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap);
 
     int t = 64;
     while (t < pb.max_row && t < 1024)
@@ -993,7 +1312,7 @@ launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
     set_smem(k_begin, cfg.smem);
     k_begin<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, d_seeds, d_x0, d_rng,
                                                       reset_solver, init_on_device,
@@ -1004,7 +1323,7 @@ void
 launch_order_init(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
     set_smem(k_order_init, cfg.smem);
     k_order_init<<<lane_count, cfg.threads, cfg.smem, s>>>(pb, pr, b, lane_first, plan);
 }
@@ -1013,7 +1332,7 @@ void
 launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
     set_smem(k_sweep, cfg.smem);
     k_sweep<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, push, obj_amp, plan);
 }
@@ -1022,7 +1341,7 @@ void
 launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
     set_smem(k_solve, cfg.smem);
     k_solve<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, plan);
 }
@@ -1031,7 +1350,7 @@ void
 launch_objective(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
     set_smem(k_objective, cfg.smem);
     k_objective<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, plan);
 }

@@ -36,15 +36,6 @@ enum
     Z_LINEAR
 };
 
-// Reduced-cost element: the union of the three solvers' rc_data
-// (itm-solver-inequalities-01.cpp:40-54, -101.cpp:41-56, -Z.cpp:44-59).
-struct __align__(16) RC
-{
-    double value;
-    int id;
-    int f;
-};
-
 // Read-only structure shared by all lanes.  P lives in CSC order (see
 // DESIGN.md): the gather for column j reads P[col_ptr[j] .. col_ptr[j+1])
 // contiguously, and the row's own entry is one of those.
@@ -56,6 +47,7 @@ struct DevProblem
     int n_obj;
     int obj_any_order; // objective sums are exact in any order
     int need_z;
+    int tail_rows; // rows whose select_variables scan can read R[r_size]
     double cost_constant;
 
     const int* row_ptr;    // [m+1]
@@ -121,14 +113,13 @@ struct DevBatch
     double* pi;      // [lanes][m]
     uint32_t* x;     // [lanes][xw32]
     uint32_t* bestx; // [lanes][xw32]
-    RC* R;           // [lanes][max_row + 2]
+    double* Rv;      // [lanes][max_row + 2] values left in the slots of the reference's R
     int* oR;         // [lanes][order_cap]
     int2* mo;        // [lanes][order_cap]
     LaneCtl* ctl;    // [lanes]
     double* kappa;   // [lanes] input of bxg_batch_sweep
-    // scratch used when a row does not fit the shared-memory budget
-    double* g_pown;  // [lanes][max_row] or nullptr
-    int* g_opos;     // [lanes][max_row] or nullptr
+    // row scratch when it does not fit the shared-memory budget, else nullptr
+    unsigned char* g_scratch; // [lanes][lane_scratch_bytes]
 };
 
 struct LaunchCfg
@@ -136,9 +127,11 @@ struct LaunchCfg
     int threads;
     size_t smem;
     int pi_in_smem, x_in_smem, r_in_smem;
+    int sort_cap;
 };
 
 LaunchCfg plan_launch(const DevProblem& pb, int device);
+size_t lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg);
 
 void launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   const uint32_t* d_seeds, const uint32_t* d_x0,

@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- constraint-updates/s of the B200 sweep engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+A *step* is one pass of the hot path over one batch: `lanes` independent
+restarts (one Solver instance each: P, pi, x, random engine) of the workload,
+each running the reference's solver_functor loop (lib/src/itm-solver-common.hpp
+:135-225) for `limit` sweeps -- bxg_batch_begin + bxg_batch_solve through the
+C ABI (include/bxg.h).  Workload at N=1 = BASELINE.json configs[1]: the
+SPP-shaped 500 x 10 000 set-partitioning instance, 1024 batched restarts.
+For N>1 every rank runs its own `lanes` restarts (weak scaling, no data-path
+collective: restarts are independent; only the final best-objective reduce
+goes over NCCL).
+
+The JSON line carries the device-resident number (`value`), the end-to-end
+number through the C ABI with host buffers (`e2e`), the roofline of the
+dominant kernel and the reference's CPU implementation timed on this box's
+host cores (`cpu_baseline`, rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "constraint-updates/s"
+UNIT = "updates/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="spp", choices=["spp", "scp", "csplib022", "rail-small"])
+    ap.add_argument("--lanes", type=int, default=1024, help="restarts per GPU per step")
+    ap.add_argument("--limit", type=int, default=100, help="sweeps per restart (solver_parameters.limit)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-lanes", type=int, default=0, help="restarts in the CPU sample (0 = 2 x cores)")
+    return ap.parse_args()
+
+
+def make_instance(name):
+    from baryonyx_b200 import synth
+
+    if name == "spp":
+        return synth.spp(), "SPP-shaped 500x10000 set partitioning (BASELINE configs[1])"
+    if name == "scp":
+        return synth.scp(), "scp41-shaped 200x1000 set covering (BASELINE configs[0])"
+    if name == "csplib022":
+        return synth.csplib022(), "csplib022-shaped 30x50000, 101 solver (BASELINE configs[2])"
+    if name == "rail-small":
+        return synth.rail(m=1071, n=273152), "rail4284-shaped at 1/4 scale"
+    raise ValueError(name)
+
+
+def bench_params(args, mod):
+    """solver_parameters of the bench: the reference's defaults except `limit`."""
+    p = mod.default_params()
+    p.limit = args.limit
+    return mod.clamp_params(p)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
+            if k in d:
+                return float(d[k]), "measured"
+    except Exception:
+        pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="bx_clocks_", suffix=".csv")
+            self.f = os.fdopen(fd, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    c = [t.strip() for t in line.split(",")]
+                    if len(c) < 8:
+                        continue
+                    try:
+                        sm.append(float(c[1]))
+                        mx.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for nm, v in zip(names, c[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference (oracle/_ref) when its
+# prebuilt library is present, else the C restatement (oracle/liboracle.so)
+# ---------------------------------------------------------------------------
+def cpu_solve_sample(inst, args, n_lanes, seed0):
+    """Runs `n_lanes` restarts of the bench workload on the host cores with the
+    reference's own solve_problem<> (counting Solver subclass), one restart
+    per worker thread at a time.  Returns (updates, sweeps, seconds, kind,
+    threads)."""
+    from baryonyx_b200 import synth
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, n_lanes)
+    seeds = [seed0 + i for i in range(n_lanes)]
+    results = [None] * n_lanes
+
+    if po.ref_available(fast=True):
+        kind = "reference"
+        p = po.default_params()
+        p.limit = args.limit
+        fd, path = tempfile.mkstemp(suffix=".lp", prefix="bx_bench_")
+        os.close(fd)
+        synth.write_lp(inst, path)
+        pb = po.RefProblem(path, p, fast=True)
+        os.unlink(path)
+        solve = lambda s: pb.solve(s)
+    else:
+        kind = "port"
+        po.build_oracle()
+        cp = bench_params(args, po)
+        pb = po.OracleProblem(inst)
+        solve = lambda s: pb.solve(cp, s)
+
+    nxt = [0]
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= n_lanes:
+                return
+            results[i] = solve(seeds[i])
+
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=worker) for _ in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    pb.close()
+    upd = sum(r["updates"] for r in results)
+    swp = sum(r["sweeps"] for r in results)
+    return upd, swp, dt, kind, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    inst, wname = make_instance(args.workload)
+    cores = os.cpu_count() or 1
+    n_lanes = args.cpu_lanes or 2 * cores
+    for _ in range(args.warmup):
+        cpu_solve_sample(inst, args, min(n_lanes, cores), 1)
+    upd = 0
+    sec = 0.0
+    kind = threads = None
+    for s in range(args.steps):
+        u, _, dt, kind, threads = cpu_solve_sample(inst, args, n_lanes, 1 + s * n_lanes)
+        upd += u
+        sec += dt
+    value = upd / sec
+    sample = f"{n_lanes} of {args.lanes} restarts per step, limit={args.limit}, {threads} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wname, "lanes_per_gpu": args.lanes, "limit": args.limit,
+                   "mode": "solve (solver_functor per restart)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# the engine
+# ---------------------------------------------------------------------------
+def pinned_like(a):
+    """Copy of a numpy array in pinned host memory (a numpy view on a torch
+    pinned tensor; the tensor is kept alive by the returned object's base)."""
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).clone().pin_memory()
+    v = t.numpy()
+    pinned_like.keep.append(t)
+    return v
+
+
+pinned_like.keep = []
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    from baryonyx_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    inst, wname = make_instance(args.workload)
+    cp = bench_params(args, capi)
+    L = args.lanes
+    nnz = int(inst["row_ptr"][-1])
+
+    pb = capi.Problem(inst, device=local)
+    bt = pb.batch(L, cp)
+    info = bt.info()
+
+    def seeds_of(step):
+        base = 1 + (rank * 1_000_003 + step) * L
+        return (np.arange(L, dtype=np.uint64) + base).astype(np.uint32)
+
+    def one_step(step):
+        bt.begin(seeds_of(step), reset_solver=True)
+        ms = bt.last_ms()
+        out = bt.solve()
+        return ms, bt.last_ms(), out
+
+    for s in range(args.warmup):
+        one_step(s)
+
+    bt.reset_counters()
+    launches0 = bt.launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    solve_ms = 0.0
+    for s in range(args.steps):
+        a, b, out = one_step(args.warmup + s)
+        dev_ms += a + b
+        solve_ms += b
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = bt.counters()
+    launches = bt.launches() - launches0
+    lane, best_value, best_rem = bt.argbest()
+
+    # max over ranks of the step time, sum over ranks of the work
+    t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(cnt["updates"]), float(cnt["sweeps"]), cnt["algorithmic_bytes"],
+                      float(launches)], dtype=torch.float64, device="cuda")
+    # incumbent exchange: best objective over ranks
+    key = torch.tensor([float(best_rem), best_value if best_rem == 0 else float("inf")],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    wall_max, dev_ms_max = t.tolist()
+    updates, sweeps, alg_bytes, launches_all = w.tolist()
+
+    # ---- end to end through the C ABI with host buffers ---------------------
+    e2e = None
+    if not args.no_e2e:
+        keys = ("row_ptr", "col", "factor", "cmin", "cmax", "obj_var", "obj_factor")
+        hinst = dict(inst)
+        for k in keys:
+            hinst[k] = pinned_like(inst[k])
+        h2d = sum(hinst[k].nbytes for k in keys) + 4 * L
+        d2h = 0
+        e2e_updates = 0
+        barrier()
+        te = time.perf_counter()
+        for s in range(args.steps):
+            pb2 = capi.Problem(hinst, device=local)
+            bt2 = pb2.batch(L, cp)
+            bt2.begin(pinned_like(seeds_of(args.warmup + s)), reset_solver=True)
+            out2 = bt2.solve()
+            ln, _, _ = bt2.argbest()
+            xb = bt2.best(ln)
+            e2e_updates += bt2.counters()["updates"]
+            d2h = xb.nbytes + sum(v.nbytes for v in out2.values())
+            bt2.close()
+            pb2.close()
+        barrier()
+        e2e_wall = time.perf_counter() - te
+        te_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+        eu_t = torch.tensor([float(e2e_updates)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(eu_t, op=dist.ReduceOp.SUM)
+        e2e = {"value": eu_t.item() / te_t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * te_t.item() / args.steps}
+
+    bt.close()
+    pb.close()
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        # dominant kernel = k_solve (one launch per step per GPU); bytes and
+        # time below are per launch on this rank
+        per_launch_bytes = cnt["algorithmic_bytes"] / args.steps
+        per_launch_s = solve_ms / args.steps / 1e3
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": updates / wall_max, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps,
+            "device_ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wname, "lanes_per_gpu": L, "limit": args.limit,
+                       "mode": "solve (solver_functor per restart)", "m": inst["m"], "n": inst["n"],
+                       "nnz": nnz, "l2": "inputs larger than L2 (P is %.0f MB per GPU)" % (L * nnz * 8 / 1e6),
+                       "device_bytes": info["device_bytes"]},
+            "sweeps_per_s": sweeps / wall_max,
+            "best": {"remaining": key[0].item(), "value": key[1].item()},
+            "roofline": {"bound": "hbm", "kernel": "k_solve", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                         "traffic": None, "bytes_per_launch": per_launch_bytes,
+                         "ms_per_launch": 1e3 * per_launch_s},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_lanes or 2 * cores
+            u, _, dt, kind, threads = cpu_solve_sample(inst, args, n_cpu, 1)
+            line["cpu_baseline"] = {
+                "value": u / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": f"{n_cpu} of {L} restarts, limit={args.limit}, {threads} host threads, {dt:.1f}s",
+            }
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_engine(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
