@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbaryonyx_b200.so")
+LIB_PATH = os.environ.get("BXG_LIB") or os.path.join(HERE, "libbaryonyx_b200.so")
 
 
 class Params(C.Structure):

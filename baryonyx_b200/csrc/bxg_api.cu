@@ -91,7 +91,13 @@ struct bxg_problem
 
     // host copies (taps, host-side initialisation policies)
     std::vector<int> row_ptr, row_col, row_a, row_cscpos;
-    std::vector<int> col_ptr, csc_row, csc_a, csc_val;
+    std::vector<int> col_ptr, csc_row, csc_a, csc_val, csc_rs;
+    std::vector<int4> row_info;
+    std::vector<int2> gp;
+    std::vector<RowHdr> row_hdr;
+    int p95_row = 0;
+    std::vector<int> row_gptr, row_eptr;
+    int max_col = 0, max_S = 0;
     std::vector<int> cmin, cmax, bmin, bmax, row_neg, ztype;
     std::vector<float> row_bytes;
     std::vector<int> obj_var;
@@ -101,7 +107,11 @@ struct bxg_problem
     int tail_rows = 0; // rows that can read R[r_size]
 
     DevBuf<int> d_row_ptr, d_row_col, d_row_a, d_row_cscpos, d_col_ptr, d_csc_row,
-      d_csc_a, d_bmin, d_bmax, d_row_neg, d_ztype, d_obj_var;
+      d_csc_a, d_csc_rs, d_bmin, d_bmax, d_row_neg, d_ztype, d_obj_var;
+    DevBuf<int4> d_row_info;
+    DevBuf<int2> d_gp;
+    DevBuf<RowHdr> d_row_hdr;
+    DevBuf<int> d_row_gptr, d_row_eptr;
     DevBuf<float> d_row_bytes;
     DevBuf<double> d_obj_factor, d_cost;
 
@@ -121,7 +131,7 @@ struct bxg_batch
     DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_Rv;
     DevBuf<unsigned char> d_scratch;
     DevBuf<uint32_t> d_x, d_bestx, d_seeds, d_x0, d_rng0;
-    DevBuf<int> d_oR;
+    DevBuf<int> d_oR, d_act;
     DevBuf<int2> d_mo;
     DevBuf<LaneCtl> d_ctl;
 
@@ -431,6 +441,46 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     for (int k = 0; k != m; ++k)
         pb->max_row = std::max(pb->max_row, row_ptr[k + 1] - row_ptr[k]);
 
+    // per row element: its column's CSC range, its own CSC position, its
+    // column -- one 16-byte load instead of a three-level index chain
+    pb->row_info.resize(nnz);
+    pb->csc_rs.resize(nnz);
+    for (int e = 0; e != nnz; ++e) {
+        const int j = col[e];
+        pb->row_info[e] = make_int4(pb->col_ptr[j], pb->col_ptr[j + 1], pb->row_cscpos[e], j);
+    }
+    for (int t = 0; t != nnz; ++t)
+        pb->csc_rs[t] = (pb->csc_row[t] << 1) | (pb->csc_a[t] < 0 ? 1 : 0);
+
+    // expanded column entries of every row (see DevProblem::gp)
+    {
+        long long total = 0;
+        for (int j = 0; j != n; ++j) {
+            const long long c = pb->col_ptr[j + 1] - pb->col_ptr[j];
+            total += c * c;
+            pb->max_col = std::max(pb->max_col, static_cast<int>(c));
+        }
+        if (total > 2000000000ll)
+            return fail(BXG_E_MEMORY, "bxg_problem_create: expanded column index exceeds 2^31 entries");
+        pb->gp.resize(static_cast<size_t>(total));
+        pb->row_gptr.assign(m + 1, 0);
+        pb->row_eptr.resize(nnz);
+        size_t g = 0;
+        for (int k = 0; k != m; ++k) {
+            pb->row_gptr[k] = static_cast<int>(g);
+            int local = 0;
+            for (int e = row_ptr[k]; e != row_ptr[k + 1]; ++e) {
+                pb->row_eptr[e] = local;
+                const int j = col[e];
+                for (int t = pb->col_ptr[j]; t != pb->col_ptr[j + 1]; ++t)
+                    pb->gp[g++] = make_int2(t, pb->csc_rs[t]);
+                local += pb->col_ptr[j + 1] - pb->col_ptr[j];
+            }
+            pb->max_S = std::max(pb->max_S, local);
+        }
+        pb->row_gptr[m] = static_cast<int>(g);
+    }
+
     // Solver bounds (constructor bodies cited in bxg.h)
     pb->bmin.resize(m);
     pb->bmax.resize(m);
@@ -500,6 +550,25 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
         pb->row_bytes[k] = static_cast<float>(bytes);
     }
 
+    pb->row_hdr.resize(m);
+    {
+        std::vector<int> lens(m);
+        for (int k = 0; k != m; ++k) {
+            RowHdr& h = pb->row_hdr[k];
+            h.r0 = row_ptr[k];
+            h.r_size = row_ptr[k + 1] - row_ptr[k];
+            h.g0 = pb->row_gptr[k];
+            h.S = pb->row_gptr[k + 1] - pb->row_gptr[k];
+            h.bmin = pb->bmin[k];
+            h.bmax = pb->bmax[k];
+            h.c_size = pb->row_neg[k];
+            h.bytes = pb->row_bytes[k];
+            lens[k] = h.r_size;
+        }
+        std::sort(lens.begin(), lens.end());
+        pb->p95_row = lens[std::min<size_t>(m - 1, static_cast<size_t>(0.95 * m))];
+    }
+
     // default_cost_type constructor, itm-common.hpp:1006-1016
     pb->obj_var.assign(obj_var, obj_var + n_obj);
     pb->obj_factor.assign(obj_factor, obj_factor + n_obj);
@@ -527,6 +596,12 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     CUDA_TRY(pb->d_row_cscpos.upload(pb->row_cscpos));
     CUDA_TRY(pb->d_col_ptr.upload(pb->col_ptr));
     CUDA_TRY(pb->d_csc_row.upload(pb->csc_row));
+    CUDA_TRY(pb->d_csc_rs.upload(pb->csc_rs));
+    CUDA_TRY(pb->d_row_info.upload(pb->row_info));
+    CUDA_TRY(pb->d_gp.upload(pb->gp));
+    CUDA_TRY(pb->d_row_hdr.upload(pb->row_hdr));
+    CUDA_TRY(pb->d_row_gptr.upload(pb->row_gptr));
+    CUDA_TRY(pb->d_row_eptr.upload(pb->row_eptr));
     if (pb->family != FAM_01) {
         CUDA_TRY(pb->d_row_a.upload(pb->row_a));
         CUDA_TRY(pb->d_csc_a.upload(pb->csc_a));
@@ -545,6 +620,13 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.n = n;
     d.nnz = nnz;
     d.max_row = pb->max_row;
+    d.max_col = pb->max_col;
+    d.p95_row = pb->p95_row;
+    d.row_hdr = pb->d_row_hdr.p;
+    d.max_S = pb->max_S;
+    d.gp = pb->d_gp.p;
+    d.row_gptr = pb->d_row_gptr.p;
+    d.row_eptr = pb->d_row_eptr.p;
     d.family = pb->family;
     d.maximize = pb->maximize;
     d.xw32 = 2 * (n / 64 + 1);
@@ -556,6 +638,8 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.row_ptr = pb->d_row_ptr.p;
     d.row_col = pb->d_row_col.p;
     d.row_cscpos = pb->d_row_cscpos.p;
+    d.row_info = pb->d_row_info.p;
+    d.csc_rs = pb->d_csc_rs.p;
     d.row_a = pb->family != FAM_01 ? pb->d_row_a.p : nullptr;
     d.col_ptr = pb->d_col_ptr.p;
     d.csc_row = pb->d_csc_row.p;
@@ -689,6 +773,8 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(b->d_x.alloc(L * pb->dev.xw32));
     CUDA_TRY(b->d_bestx.alloc(L * pb->dev.xw32));
     CUDA_TRY(b->d_Rv.alloc(L * (pb->max_row + 2)));
+    CUDA_TRY(b->d_act.alloc(L * m));
+    CUDA_TRY(cudaMemset(b->d_act.p, 0, b->d_act.bytes()));
     CUDA_TRY(b->d_oR.alloc(L * b->order_cap));
     CUDA_TRY(b->d_mo.alloc(L * b->order_cap));
     CUDA_TRY(b->d_ctl.alloc(L));
@@ -712,6 +798,7 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     d.x = b->d_x.p;
     d.bestx = b->d_bestx.p;
     d.Rv = b->d_Rv.p;
+    d.act = b->d_act.p;
     d.oR = b->d_oR.p;
     d.mo = b->d_mo.p;
     d.ctl = b->d_ctl.p;
@@ -752,7 +839,7 @@ bxg_batch_info(const bxg_batch* b, int* n_lanes, double* delta, double* theta,
     if (device_bytes)
         *device_bytes = static_cast<int64_t>(
           b->d_P.bytes() + b->d_pi.bytes() + b->d_x.bytes() + b->d_bestx.bytes() +
-          b->d_Rv.bytes() + b->d_oR.bytes() + b->d_mo.bytes() + b->d_ctl.bytes() +
+          b->d_Rv.bytes() + b->d_act.bytes() + b->d_oR.bytes() + b->d_mo.bytes() + b->d_ctl.bytes() +
           b->d_scratch.bytes());
     return BXG_OK;
 }

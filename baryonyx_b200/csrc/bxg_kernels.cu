@@ -22,10 +22,16 @@
 #include <climits>
 #include <math_constants.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace bxg {
 
 namespace {
+
+// The CTA's dynamic shared memory: [Lane][Shared][row scratch][R values][pi]
+// [activities][x].  Views built from this symbol keep their address space, so
+// the hot path compiles to LDS/STS/ATOMS instead of generic accesses.
+extern __shared__ __align__(16) unsigned char g_smem[];
 
 struct Shared
 {
@@ -36,13 +42,17 @@ struct Shared
     int list_len;
     int order_state;
     int tmp_i;
-    int slow; // the current row takes the single-thread path
-    int n_pre;
+    int slow; // the current row goes to the single-thread path
     double d;
+    double kk; // kappa / (1 - kappa) of the current sweep
     double tmp_d;
     double red[32];
     int redi[32];
+    unsigned long long redk[32][2];
 };
+
+struct Lane;
+__host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 struct Lane
 {
@@ -51,23 +61,53 @@ struct Lane
     double* P;
     double* pi;
     uint32_t* x;
+    int* act; // [m] row activities sum a_kj x_j, kept up to date by the updates
     // reduced-cost scratch of the current row
-    unsigned long long* key0; // [max_row]   sort keys in row order
-    unsigned long long* sk;   // [sort_cap]  keys being sorted
+    unsigned long long* key0; // [max_row]   value bits / sort keys in row order
+    unsigned long long* sk;   // [sort_cap]  keys being sorted; doubles as the tie table
     int* sid;                 // [sort_cap]  position in the row, moved with sk
     double* Rv;               // [max_row+2] value left at each slot of the reference's R
-    double* pown;
-    int* opos;
-    int* viol;
+    double* pown;             // [max_row+1] theta-decayed P of the row's own entries
+    double* stage;            // [2][stage_cap] P and pi terms of the entries being summed
+    int stage_cap;
     int* oR;
     int2* mo;
     LaneCtl* ctl;
     Shared* sh;
-    int sort_cap; // the CTA-wide sort handles rows up to this length
+    int all_smem;  // pi, x and the row scratch are all in shared memory
+    // byte offsets into g_smem of the views that live there (all_smem)
+    int o_stage, o_key0, o_sk, o_pown, o_pi, o_act, o_x;
+    int sort_cap;  // the CTA-wide sort handles rows up to this length (0 = none)
+    int tab_bits;  // log2 of the tie-table size (32-bit entries laid over sk)
+    int tab_gen;   // generation stamp of the tie table (uniform over the CTA)
+    int tab_dirty; // the table must be cleared before its next use
     unsigned long long updates;
     unsigned long long sweeps;
     double alg_bytes;
 };
+
+constexpr size_t kLaneBytes = align16(sizeof(Lane));
+
+// A lane view: the shared-memory window when the plan put it there (SM), the
+// generic pointer otherwise.
+template<bool SM, typename T>
+__device__ __forceinline__ T*
+view(T* generic, int offset)
+{
+    return SM ? reinterpret_cast<T*>(g_smem + offset) : generic;
+}
+
+__device__ __forceinline__ Lane&
+the_lane()
+{
+    return *reinterpret_cast<Lane*>(g_smem);
+}
+
+__device__ __forceinline__ Shared*
+the_shared()
+{
+    return reinterpret_cast<Shared*>(g_smem + kLaneBytes);
+}
 
 __device__ __forceinline__ int
 xbit(const uint32_t* x, int i)
@@ -167,23 +207,41 @@ select_window(int family, int r_size, int c_size, int bkmin, int bkmax, int& lo,
     }
 }
 
-// Scalar part of affect (itm-common.hpp:382-467): pi_k and the preference
-// step d from the values around the selection boundary.  One thread.
+// Scalar part of affect (itm-common.hpp:382-467): the preference step d and
+// the new pi_k from the values around the selection boundary.  Pure.
+__device__ __forceinline__ double
+affect_step(double delta, double kk, double old_pi, int selected, int r_size, double v0,
+            double vsel, double vnext, double& new_pi, bool& pi_moves)
+{
+    // kk = kappa / (1 - kappa), once per sweep; x / 2 is written x * 0.5
+    // (the same correctly rounded value)
+    double d = delta;
+    pi_moves = false;
+    new_pi = old_pi;
+    if (selected < 0) {
+        d = __dadd_rn(d, __dmul_rn(kk, __dmul_rn(v0, 0.5)));
+    } else if (selected + 1 >= r_size) {
+        d = __dadd_rn(d, __dmul_rn(kk, __dmul_rn(vsel, 1.5)));
+    } else {
+        new_pi = __dadd_rn(old_pi, __dmul_rn(__dadd_rn(vsel, vnext), 0.5));
+        pi_moves = true;
+        d = __dadd_rn(d, __dmul_rn(kk, __dsub_rn(vnext, vsel)));
+    }
+    return d;
+}
+
+// One thread: applies affect's scalars to the lane and publishes selected / d.
 __device__ __forceinline__ void
 affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0, double vsel,
                double vnext)
 {
     const double old_pi = L.pi[k];
-    const double kk = __ddiv_rn(kappa, __dsub_rn(1.0, kappa));
-    double d = L.pr->delta;
-    if (selected < 0) {
-        d = __dadd_rn(d, __dmul_rn(kk, __ddiv_rn(v0, 2.0)));
-    } else if (selected + 1 >= r_size) {
-        d = __dadd_rn(d, __dmul_rn(kk, __dmul_rn(vsel, 1.5)));
-    } else {
-        const double npi = __dadd_rn(old_pi, __ddiv_rn(__dadd_rn(vsel, vnext), 2.0));
+    double npi;
+    bool moves;
+    const double d =
+      affect_step(L.pr->delta, L.sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
+    if (moves) {
         L.pi[k] = npi;
-        d = __dadd_rn(d, __dmul_rn(kk, __dsub_rn(vnext, vsel)));
         if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
             L.sh->pi_changed = 1;
     }
@@ -193,9 +251,10 @@ affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0
 
 // Single-thread statement of calculator_sort + select_variables on the row:
 // the exact libstdc++ sort and shuffle permutations.  Used when the parallel
-// path cannot decide the row (ties across the selection boundary, NaN, -0.0).
+// paths cannot decide the row (ties across the selection boundary, NaN, -0.0,
+// rows longer than the shared-memory sort).
 template<typename Less>
-__device__ void
+__device__ __noinline__ void
 row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
 {
     const DevProblem& pb = *L.pb;
@@ -227,8 +286,8 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
         seq_shuffle(a, ret, i - ret, rng);
     }
 
-    const int c_size = pb.family == FAM_101 ? pb.row_neg[k] : 0;
-    const int bkmin = pb.bmin[k], bkmax = pb.bmax[k];
+    const int c_size = pb.family == FAM_101 ? pb.row_hdr[k].c_size : 0;
+    const int bkmin = pb.row_hdr[k].bmin, bkmax = pb.row_hdr[k].bmax;
     int selected;
     if (bkmin == bkmax) {
         const int b = bkmin + c_size;
@@ -254,9 +313,9 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
 }
 
 // Bitonic sort of sk[0..n2) (ascending) carrying sid, by the whole CTA.  n2
-// is a power of two.  Strides below 64 stay inside the 64 elements one warp
+// is a power of two.  Strides up to 32 stay inside the 64 elements one warp
 // owns, so only the wide strides need a CTA barrier.
-__device__ void
+__device__ __noinline__ void
 cta_bitonic_sort(unsigned long long* sk, int* sid, int n2)
 {
     const int tid = threadIdx.x, T = blockDim.x;
@@ -288,177 +347,48 @@ cta_bitonic_sort(unsigned long long* sk, int* sid, int n2)
     __syncthreads();
 }
 
-// One constraint update (the loop body of compute_update_row /
-// push_and_compute_update_row).  Called by all threads of the CTA.
-__device__ void
-update_row(Lane& L, int k, double kappa, int push, double obj_amp)
+// Parallel statement of calculator_sort + select_variables: the whole CTA
+// sorts the keys, the shuffle draws are accounted with the LCG jump-ahead
+// (they do not depend on the elements), one thread walks the window of
+// select_variables.  Falls back to row_select_exact (sh->slow) when equal
+// values straddle the selection boundary.  key0 must hold keys.
+__device__ __noinline__ void
+row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
 {
     const DevProblem& pb = *L.pb;
-    const DevParams& pr = *L.pr;
     const int tid = threadIdx.x, T = blockDim.x;
-    const int r0 = pb.row_ptr[k];
-    const int r_size = pb.row_ptr[k + 1] - r0;
-    const double theta = pr.theta;
-    const double* __restrict__ cost = pr.cost;
     const bool maximize = pb.maximize != 0;
 
-    if (tid == 0) {
-        L.sh->slow = 0;
-        L.alg_bytes += pb.row_bytes[k];
+    for (int i = tid; i < n2; i += T) {
+        L.sk[i] = i < r_size ? L.key0[i] : ~0ull;
+        L.sid[i] = i;
     }
     __syncthreads();
+    cta_bitonic_sort(L.sk, L.sid, n2);
 
-    // ---- A: theta decay + reduced costs (compute_reduced_costs) ----------
-    int odd = 0;   // NaN or -0.0 seen by this thread
-    int n_pre = 0; // values that neither stop the scan nor are zero
-    for (int i = tid; i < r_size; i += T) {
-        const int e = r0 + i;
-        const int j = pb.row_col[e];
-        const int c0 = pb.col_ptr[j], c1 = pb.col_ptr[j + 1];
-        double pown = 0.0;
-        int opos = c0;
-        double val;
+    // equal keys next to each other = a run random_shuffle_unique shuffles
+    int tie = 0;
+    for (int p = tid + 1; p < r_size; p += T)
+        tie |= (L.sk[p] == L.sk[p - 1]);
+    const bool has_tie = __syncthreads_or(tie) != 0;
+    const uint32_t rng0 = L.sh->rng;
+    int total_draws = 0;
+    int reject = 0;
 
-        if (pb.family == FAM_01) {
-            double sum_pi = 0.0, sum_p = 0.0;
-            for (int t = c0; t < c1; ++t) {
-                const int rw = pb.csc_row[t];
-                double p = L.P[t];
-                if (rw == k) {
-                    p = __dmul_rn(p, theta);
-                    pown = p;
-                    opos = t;
-                }
-                sum_pi = __dadd_rn(sum_pi, L.pi[rw]);
-                sum_p = __dadd_rn(sum_p, p);
-            }
-            val = __dsub_rn(__dsub_rn(cost[j], sum_pi), sum_p);
-            if (push)
-                val = __dadd_rn(val, __dmul_rn(obj_amp, cost[i]));
-        } else {
-            double sum_pi = 0.0, sum_p = 0.0;
-            for (int t = c0; t < c1; ++t) {
-                const int rw = pb.csc_row[t];
-                const double a = (double)pb.csc_a[t];
-                double p = L.P[t];
-                if (rw == k) {
-                    p = __dmul_rn(p, theta);
-                    pown = p;
-                    opos = t;
-                }
-                sum_pi = __dadd_rn(sum_pi, __dmul_rn(a, L.pi[rw]));
-                sum_p = __dadd_rn(sum_p, __dmul_rn(a, p));
-            }
-            val = __dsub_rn(__dsub_rn(cost[j], sum_pi), sum_p);
-            if (pb.row_a[e] < 0)
-                val = -val;
-            if (push)
-                val = __dadd_rn(val, __dmul_rn(obj_amp, cost[j]));
-        }
-
-        if (val != val || (val == 0.0 && __double_as_longlong(val) < 0))
-            odd = 1;
-        if (val != 0.0 && !(maximize ? val < 0 : val > 0))
-            ++n_pre;
-        // raw bits here; rewritten as keys below once the mode is known
-        L.key0[i] = (unsigned long long)__double_as_longlong(val);
-        L.pown[i] = pown;
-        L.opos[i] = opos;
-    }
-    const bool raw = __syncthreads_or(odd) != 0;
-
-    int n2 = 2;
-    while (n2 < r_size)
-        n2 <<= 1;
-
-    if (raw || r_size < 2 || n2 > L.sort_cap) {
-        if (!raw)
-            for (int i = tid; i < r_size; i += T)
-                L.key0[i] = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
-        __syncthreads();
-        if (tid == 0)
-            L.sh->slow = 1;
-    } else {
-        // ---- B: parallel order + selection ---------------------------------
-        for (int i = tid; i < n2; i += T) {
-            unsigned long long key = ~0ull;
-            if (i < r_size) {
-                key = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
-                L.key0[i] = key;
-            }
-            L.sk[i] = key;
-            L.sid[i] = i;
-        }
-        // block count of n_pre
-#pragma unroll
-        for (int o = 16; o; o >>= 1)
-            n_pre += __shfl_xor_sync(0xffffffffu, n_pre, o);
-        if ((tid & 31) == 0)
-            L.sh->redi[tid >> 5] = n_pre;
-        __syncthreads();
-        cta_bitonic_sort(L.sk, L.sid, n2);
-
-        // equal keys next to each other = a run random_shuffle_unique shuffles
-        int tie = 0;
-        for (int p = tid + 1; p < r_size; p += T)
-            tie |= (L.sk[p] == L.sk[p - 1]);
-        const bool has_tie = __syncthreads_or(tie) != 0;
-        const uint32_t rng0 = L.sh->rng;
-        int total_draws = 0;
-        int reject = 0;
-
-        if (has_tie) {
-            // Draws of all the std::shuffle calls, in sorted order.  A run of
-            // n equal keys starting at a draws floor(n/2) numbers: the element
-            // at odd offset o owns draw number (o-1)/2 (n odd) or o/2 (n even,
-            // where offset 1 owns the single-swap draw).  Its index in the
-            // row's draw sequence is the count of odd offsets before it.
-            const int C = (r_size + T - 1) / T;
-            const int p0 = min(r_size, tid * C), p1 = min(r_size, p0 + C);
-            int local = 0;
-            for (int p = p0; p < p1; ++p) {
-                const unsigned long long key = L.sk[p];
-                if (p > 0 && L.sk[p - 1] == key) {
-                    int lo = 0, hi = p; // first index holding key
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (L.sk[mid] < key)
-                            lo = mid + 1;
-                        else
-                            hi = mid;
-                    }
-                    local += (p - lo) & 1;
-                }
-            }
-            // exclusive scan of `local` over the threads
-            int incl = local;
-            const int ln = tid & 31, wp = tid >> 5;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (ln >= o)
-                    incl += v;
-            }
-            if (ln == 31)
-                L.sh->red[wp] = (double)incl;
-            __syncthreads();
-            int before = 0;
-            const int nw = T >> 5;
-            for (int w = 0; w < nw; ++w) {
-                const int v = (int)L.sh->red[w];
-                if (w < wp)
-                    before += v;
-                total_draws += v;
-            }
-            int t = before + incl - local;
-
-            for (int p = p0; p < p1; ++p) {
-                const unsigned long long key = L.sk[p];
-                const bool eq_prev = p > 0 && L.sk[p - 1] == key;
-                const bool eq_next = p + 1 < r_size && L.sk[p + 1] == key;
-                if (!eq_prev && !eq_next)
-                    continue;
-                int lo = 0, hi = p;
+    if (has_tie) {
+        // Draws of all the std::shuffle calls, in sorted order.  A run of n
+        // equal keys starting at a draws floor(n/2) numbers: with n odd the
+        // element at odd offset o owns draw (o-1)/2; with n even offset 1
+        // owns the single-swap draw 0 and even offsets o >= 2 own draw o/2.
+        // Either way the index of a draw in the row's sequence is the count
+        // of odd offsets before its owner.
+        const int C = (r_size + T - 1) / T;
+        const int p0 = min(r_size, tid * C), p1 = min(r_size, p0 + C);
+        int local = 0;
+        for (int p = p0; p < p1; ++p) {
+            const unsigned long long key = L.sk[p];
+            if (p > 0 && L.sk[p - 1] == key) {
+                int lo = 0, hi = p; // first index holding key
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if (L.sk[mid] < key)
@@ -466,101 +396,505 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
                     else
                         hi = mid;
                 }
-                const int a = lo;
-                lo = p;
-                hi = r_size; // first index above key
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (L.sk[mid] <= key)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                const int n = lo - a;
-                const int o = p - a;
-                uint32_t uerange = 0;
-                if (n & 1) {
-                    if (o & 1)
-                        uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
-                } else if (o == 1)
-                    uerange = 2u;
-                else if (o >= 2 && !(o & 1))
-                    uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
-                if (uerange) {
-                    // this draw is number t' = (count of odd offsets before p)
-                    // for o odd that is t; for o even (n even, o >= 2) the
-                    // odd offset o-1 < p is already counted in t as well
-                    const uint32_t g = lcg_mul(rng0, lcg_pow((uint64_t)t + 1u));
-                    const uint32_t scaling = 2147483645u / uerange;
-                    if (g - 1u >= uerange * scaling)
-                        reject = 1;
-                }
-                t += o & 1;
+                local += (p - lo) & 1;
             }
         }
-        const bool any_reject = has_tie && __syncthreads_or(reject) != 0;
+        // exclusive scan of `local` over the threads
+        int incl = local;
+        const int ln = tid & 31, wp = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln >= o)
+                incl += v;
+        }
+        if (ln == 31)
+            L.sh->redi[wp] = incl;
+        __syncthreads();
+        int before = 0;
+        const int nw = T >> 5;
+        for (int w = 0; w < nw; ++w) {
+            const int v = L.sh->redi[w];
+            if (w < wp)
+                before += v;
+            total_draws += v;
+        }
+        int t = before + incl - local;
 
-        if (tid == 0) {
-            uint32_t rng = rng0;
-            if (any_reject) {
-                // a uniform draw was rejected somewhere: replay the draws
-                int ret = 0;
-                int i = 1;
-                for (; i != r_size; ++i) {
-                    if (L.sk[ret] != L.sk[i]) {
-                        seq_shuffle_draws(i - ret, rng);
-                        ret = i;
-                    }
-                }
-                seq_shuffle_draws(i - ret, rng);
-            } else if (total_draws)
-                rng = lcg_mul(rng0, lcg_pow((uint64_t)total_draws));
+        for (int p = p0; p < p1; ++p) {
+            const unsigned long long key = L.sk[p];
+            const bool eq_prev = p > 0 && L.sk[p - 1] == key;
+            const bool eq_next = p + 1 < r_size && L.sk[p + 1] == key;
+            if (!eq_prev && !eq_next)
+                continue;
+            int lo = 0, hi = p;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (L.sk[mid] < key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            const int a = lo;
+            lo = p;
+            hi = r_size; // first index above key
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (L.sk[mid] <= key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            const int n = lo - a;
+            const int o = p - a;
+            uint32_t uerange = 0;
+            if (n & 1) {
+                if (o & 1)
+                    uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
+            } else if (o == 1)
+                uerange = 2u;
+            else if (o >= 2 && !(o & 1))
+                uerange = (uint32_t)(o + 1) * (uint32_t)(o + 2);
+            if (uerange) {
+                const uint32_t g = lcg_mul(rng0, lcg_pow((uint64_t)t + 1u));
+                const uint32_t scaling = 2147483645u / uerange;
+                if (g - 1u >= uerange * scaling)
+                    reject = 1;
+            }
+            t += o & 1;
+        }
+    }
+    const bool any_reject = has_tie && __syncthreads_or(reject) != 0;
 
-            int npre = 0;
-            const int nw = T >> 5;
-            for (int w = 0; w < nw; ++w)
-                npre += L.sh->redi[w];
-
-            const int c_size = pb.family == FAM_101 ? pb.row_neg[k] : 0;
-            const int bkmin = pb.bmin[k], bkmax = pb.bmax[k];
-            int selected;
-            if (bkmin == bkmax) {
-                const int b = bkmin + c_size;
-                selected = (b < r_size ? b : r_size) - 1;
-            } else {
-                int lo, hi;
-                select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
-                selected = hi - 1;
-                // the first npre sorted values neither stop nor draw
-                int i = lo;
-                if (i < npre)
-                    i = npre;
-                for (; i <= hi; ++i) {
-                    const double v = i < r_size ? value_of_key(L.sk[i], maximize) : L.Rv[r_size];
-                    if (stop_iterating_rng(v, maximize, rng)) {
-                        selected = i - 1;
-                        break;
-                    }
+    if (tid == 0) {
+        uint32_t rng = rng0;
+        if (any_reject) {
+            // a uniform draw was rejected somewhere: replay the draws
+            int ret = 0;
+            int i = 1;
+            for (; i != r_size; ++i) {
+                if (L.sk[ret] != L.sk[i]) {
+                    seq_shuffle_draws(i - ret, rng);
+                    ret = i;
                 }
             }
+            seq_shuffle_draws(i - ret, rng);
+        } else if (total_draws)
+            rng = lcg_mul(rng0, lcg_pow((uint64_t)total_draws));
 
-            if (selected >= 0 && selected + 1 < r_size && L.sk[selected] == L.sk[selected + 1]) {
-                // equal values on both sides of the boundary: which of them
-                // are selected is decided by the exact permutations
-                L.sh->slow = 1;
-            } else {
-                L.sh->rng = rng;
-                const double v0 = value_of_key(L.sk[0], maximize);
-                const double vsel = selected >= 0 ? value_of_key(L.sk[selected], maximize) : 0.0;
-                const double vnext =
-                  (selected >= 0 && selected + 1 < r_size) ? value_of_key(L.sk[selected + 1], maximize) : 0.0;
-                affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
+        const int c_size = pb.family == FAM_101 ? pb.row_hdr[k].c_size : 0;
+        const int bkmin = pb.row_hdr[k].bmin, bkmax = pb.row_hdr[k].bmax;
+        int selected;
+        if (bkmin == bkmax) {
+            const int b = bkmin + c_size;
+            selected = (b < r_size ? b : r_size) - 1;
+        } else {
+            int lo, hi;
+            select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+            selected = hi - 1;
+            // the first n_pre sorted values neither stop the scan nor draw
+            int i = lo;
+            if (i < n_pre)
+                i = n_pre;
+            for (; i <= hi; ++i) {
+                const double v = i < r_size ? value_of_key(L.sk[i], maximize) : L.Rv[r_size];
+                if (stop_iterating_rng(v, maximize, rng)) {
+                    selected = i - 1;
+                    break;
+                }
             }
+        }
+
+        if (selected >= 0 && selected + 1 < r_size && L.sk[selected] == L.sk[selected + 1]) {
+            // equal values on both sides of the boundary: which of them are
+            // selected is decided by the exact permutations
+            L.sh->slow = 1;
+        } else {
+            L.sh->slow = 0;
+            L.sh->rng = rng;
+            const double v0 = value_of_key(L.sk[0], maximize);
+            const double vsel = selected >= 0 ? value_of_key(L.sk[selected], maximize) : 0.0;
+            const double vnext =
+              (selected >= 0 && selected + 1 < r_size) ? value_of_key(L.sk[selected + 1], maximize) : 0.0;
+            affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
         }
     }
     __syncthreads();
+}
 
-    if (L.sh->slow) {
+// x / P part of affect (itm-common.hpp:404-463) for the element `id` of row k,
+// plus the row activities of the column when the bit flips.
+template<int FAM, bool SM>
+__device__ __forceinline__ void
+affect_element(Lane& L, int r0, int id, double pv, bool in, double d)
+{
+    const DevProblem& pb = *L.pb;
+    const int4 info = pb.row_info[r0 + id]; // c0, c1, own CSC position, column
+    const bool neg = FAM != FAM_01 && pb.row_a[r0 + id] < 0;
+    const bool set = in != neg;
+    double* const gP = L.P;
+    gP[info.z] = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
+
+    uint32_t* const x = view<SM>(L.x, L.o_x);
+    int* const act = view<true>(L.act, L.o_act);
+    const int j = info.w;
+    const uint32_t bit = 1u << (j & 31);
+    const bool was = (x[j >> 5] & bit) != 0;
+    if (was != set) {
+        atomicXor(&x[j >> 5], bit);
+        const int sgn = set ? 1 : -1;
+        for (int t = info.x; t < info.y; ++t) {
+            const int rs = pb.csc_rs[t];
+            if (FAM == FAM_01)
+                atomicAdd(&act[rs >> 1], sgn);
+            else if (FAM == FAM_101)
+                atomicAdd(&act[rs >> 1], (rs & 1) ? -sgn : sgn);
+            else
+                atomicAdd(&act[rs >> 1], sgn * pb.csc_a[t]);
+        }
+    }
+}
+
+// 64-bit minimum over a warp with two 32-bit REDUX steps.
+__device__ __forceinline__ unsigned long long
+warp_min_u64(unsigned long long v)
+{
+    const uint32_t hi = (uint32_t)(v >> 32);
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t lo = hi == mhi ? (uint32_t)v : 0xffffffffu;
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, lo);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
+// Top-2 merge of ascending pairs.
+__device__ __forceinline__ void
+merge_min2(unsigned long long& m1, unsigned long long& m2, unsigned long long o1,
+           unsigned long long o2)
+{
+    const unsigned long long lo = m1 < o1 ? m1 : o1;
+    const unsigned long long hi = m1 < o1 ? o1 : m1;
+    const unsigned long long s2 = m2 < o2 ? m2 : o2;
+    m1 = lo;
+    m2 = hi < s2 ? hi : s2;
+}
+
+// One constraint update (the loop body of compute_update_row /
+// push_and_compute_update_row).  Called by all threads of the CTA.
+//
+// A. compute_reduced_costs (itm-solver-inequalities-01.cpp:166-191,
+//    -101.cpp:199-233) in two stages.  Stage 1 is parallel over the column
+//    ENTRIES of the row (the expanded list gp, built once per problem): every
+//    thread loads P and pi for a strided share of the entries -- independent,
+//    coalesced loads -- applies the theta decay to the row's own entry and the
+//    +-1 factor, and parks the terms in shared memory.  Stage 2 is parallel
+//    over the row ELEMENTS: each adds its column's terms left to right in CSC
+//    order with the reference's two accumulators, so the sums are bit-equal.
+// B. selection without ordering when all values differ (the usual case once
+//    pi and P have moved): two smallest keys, or the boundary by sign.
+template<int FAM, bool SM>
+__device__ __noinline__ void
+update_row(int k, double kappa, int push, double obj_amp)
+{
+    Lane& L = the_lane();
+    const DevProblem& pb = *L.pb;
+    const DevParams& pr = *L.pr;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    const RowHdr hdr = pb.row_hdr[k];
+    const int r0 = hdr.r0;
+    const int r_size = hdr.r_size;
+    const double theta = pr.theta;
+    const bool maximize = pb.maximize != 0;
+    const double* __restrict__ cost = pr.cost;
+    // shared-memory views (the Lane block itself always lives there)
+    const int stage_cap = L.stage_cap;
+    double* const sp = view<SM>(L.stage, L.o_stage); // [stage_cap] P terms
+    double* const spi = sp + stage_cap;              // [stage_cap] pi terms
+    double* const s_pi = view<SM>(L.pi, L.o_pi);
+    unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
+    double* const pown = view<SM>(L.pown, L.o_pown);
+    double* const gP = L.P;
+    Shared* const sh = the_shared();
+    const int2* __restrict__ gp = pb.gp + hdr.g0;
+    const int S = hdr.S;
+    const int bkmin = hdr.bmin, bkmax = hdr.bmax;
+    const bool is_eq = bkmin == bkmax;
+
+    if (tid == 0)
+        L.alg_bytes += hdr.bytes;
+
+    int odd = 0;    // NaN or -0.0 seen by this thread
+    int counts = 0; // low half: values that neither stop the scan nor are zero; high half: zeros
+    // candidates of this thread: the two smallest keys (ca <= cb); for an
+    // inequality row also the largest non-stopping key (complemented, sa) and
+    // the smallest stopping key (sb)
+    unsigned long long ca = ~0ull, cb = ~0ull, sa = ~0ull, sb = ~0ull;
+
+    for (int ia = 0; ia < r_size;) {
+        // elements [ia, ib) whose entries fit the staging buffer
+        int ib = r_size;
+        const int fa = pb.row_eptr[r0 + ia];
+        int fb = S;
+        if (S - fa > stage_cap) {
+            int lo = ia + 1, hi = r_size; // last ib with eptr[ib] - fa <= cap
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (pb.row_eptr[r0 + mid] - fa <= stage_cap)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            ib = lo;
+            fb = pb.row_eptr[r0 + ib];
+        }
+
+        // stage 1: entries
+        for (int g = fa + tid; g < fb; g += 4 * T) {
+            int2 e[4];
+            double p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int gg = g + u * T;
+                e[u] = gg < fb ? gp[gg] : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                p[u] = (g + u * T) < fb ? gP[e[u].x] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int gg = g + u * T;
+                if (gg < fb) {
+                    const int row = e[u].y >> 1;
+                    double pv = p[u];
+                    if (row == k)
+                        pv = __dmul_rn(pv, theta);
+                    double a_pi = s_pi[row];
+                    if (FAM != FAM_01 && (e[u].y & 1)) {
+                        pv = -pv;
+                        a_pi = -a_pi;
+                    }
+                    sp[gg - fa] = pv;
+                    spi[gg - fa] = a_pi;
+                }
+            }
+        }
+        __syncthreads();
+
+        // stage 2: elements
+        for (int i = ia + tid; i < ib; i += T) {
+            const int4 info = pb.row_info[r0 + i]; // c0, c1, own CSC position, column
+            const int s0 = pb.row_eptr[r0 + i] - fa;
+            const int len = info.y - info.x;
+            const double cj = cost[info.w];
+            double sum_pi = 0.0, sum_p = 0.0;
+            for (int t = 0; t < len; ++t) {
+                sum_pi = __dadd_rn(sum_pi, spi[s0 + t]);
+                sum_p = __dadd_rn(sum_p, sp[s0 + t]);
+            }
+            double own = sp[s0 + (info.z - info.x)];
+            double v = __dsub_rn(__dsub_rn(cj, sum_pi), sum_p);
+            if (FAM != FAM_01 && pb.row_a[r0 + i] < 0) {
+                v = -v;
+                own = -own;
+            }
+            if (push)
+                v = __dadd_rn(v, __dmul_rn(obj_amp, FAM == FAM_01 ? cost[i] : cj));
+
+            if (v != v || (v == 0.0 && __double_as_longlong(v) < 0))
+                odd = 1;
+            const bool stop = maximize ? v < 0 : v > 0;
+            const unsigned long long key = key_of(v, maximize);
+            merge_min2(ca, cb, key, ~0ull);
+            if (!is_eq) {
+                if (v == 0.0)
+                    counts += 1 << 16;
+                else if (!stop)
+                    counts += 1;
+                if (stop)
+                    sb = key < sb ? key : sb;
+                else
+                    sa = ~key < sa ? ~key : sa;
+            }
+            key0[i] = (unsigned long long)__double_as_longlong(v);
+            pown[i] = own;
+        }
+        ia = ib;
+        if (ia < r_size)
+            __syncthreads(); // the staging buffer is reused
+    }
+
+    if (!is_eq) {
+        counts = __reduce_add_sync(0xffffffffu, counts);
+        if (ln == 0)
+            sh->redi[wp] = counts;
+    }
+    const double old_pi = s_pi[k];
+    const int tab_gen0 = L.tab_gen;
+    const int tab_dirty0 = L.tab_dirty;
+    const bool raw = __syncthreads_or(odd) != 0;
+    int n_pre = 0, n_zero = 0;
+    if (!is_eq) {
+        counts = 0;
+        for (int w = 0; w < nw; ++w)
+            counts += sh->redi[w];
+        n_pre = counts & 0xffff;
+        n_zero = counts >> 16;
+    }
+
+    const int n2 = r_size <= 2 ? 2 : 1 << (32 - __clz(r_size - 1));
+
+    // ---- B: which elements are selected ------------------------------------
+    // mode 0: exact single thread; 1: CTA sort; 2: two smallest; 3: boundary by sign
+    int mode;
+    int selected = -1;
+    if (raw || r_size < 2 || r_size > 0xffff || n2 > L.sort_cap) {
+        mode = 0;
+    } else {
+        mode = 1;
+        if (pb.tail_rows == 0) {
+            const int c_size = FAM == FAM_101 ? hdr.c_size : 0;
+            if (is_eq) {
+                const int b = bkmin + c_size;
+                selected = (b < r_size ? b : r_size) - 1;
+                if (selected <= 0)
+                    mode = 2;
+            } else if (n_zero == 0) {
+                int lo, hi;
+                select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+                const int i0 = lo > n_pre ? lo : n_pre; // first index holding a stopping value
+                selected = (i0 <= hi ? i0 : hi) - 1;
+                if (selected + 1 == n_pre)
+                    mode = 3;
+                else if (selected <= 0)
+                    mode = 2;
+            }
+        }
+    }
+
+    if (mode >= 2) {
+        // No order is needed as long as all values differ: look for equal
+        // values with a table of row positions hashed by key (32-bit entries
+        // laid over sk, stamped with a generation so it is cleared rarely).
+        uint32_t* tab = reinterpret_cast<uint32_t*>(view<SM>(L.sk, L.o_sk));
+        const int tab_bits = L.tab_bits;
+        int tab_gen = tab_gen0;
+        if (tab_dirty0 || tab_gen >= 0xffff) {
+            for (int i = tid; i < (1 << tab_bits); i += T)
+                tab[i] = 0u;
+            tab_gen = 0;
+            __syncthreads();
+            if (tid == 0)
+                L.tab_dirty = 0;
+        }
+        const uint32_t gen = (uint32_t)++tab_gen;
+        const uint32_t mask = (1u << tab_bits) - 1u;
+        int dup = 0;
+        for (int i = tid; i < r_size; i += T) {
+            const unsigned long long bits = key0[i];
+            uint32_t h = ((uint32_t)bits ^ (uint32_t)(bits >> 32)) * 0x9E3779B1u;
+            h = (h >> (32 - tab_bits)) & mask;
+            const uint32_t mine = (gen << 16) | (uint32_t)(i + 1);
+            for (;;) {
+                uint32_t cur = tab[h];
+                if ((cur >> 16) != gen) {
+                    const uint32_t prev = atomicCAS(&tab[h], cur, mine);
+                    if (prev == cur)
+                        break;
+                    cur = prev;
+                    if ((cur >> 16) != gen)
+                        continue; // lost a race against a stale entry: look again
+                }
+                const int other = (int)(cur & 0xffffu) - 1;
+                if (key0[other] == bits) {
+                    dup = 1;
+                    break;
+                }
+                h = (h + 1u) & mask;
+            }
+        }
+
+        // candidates over the warp: mode 2 = the two smallest keys, mode 3 =
+        // (largest non-stopping key, complemented; smallest stopping key)
+        unsigned long long a, b;
+        if (mode == 2) {
+            a = warp_min_u64(ca);
+            // one holder of the minimum gives it up, everybody else keeps theirs
+            const unsigned holders = __ballot_sync(0xffffffffu, ca == a);
+            const bool gives = ca == a && (holders & ((1u << ln) - 1u)) == 0;
+            b = warp_min_u64(gives ? cb : ca);
+        } else {
+            a = warp_min_u64(sa);
+            b = warp_min_u64(sb);
+        }
+        if (ln == 0) {
+            sh->redk[wp][0] = a;
+            sh->redk[wp][1] = b;
+        }
+        const bool any_dup = __syncthreads_or(dup) != 0;
+        if (tid == 0)
+            L.tab_gen = tab_gen;
+        if (any_dup)
+            mode = 1; // equal values: their runs draw from the engine
+        else {
+            a = sh->redk[0][0];
+            b = sh->redk[0][1];
+            for (int w = 1; w < nw; ++w) {
+                const unsigned long long oa = sh->redk[w][0], ob = sh->redk[w][1];
+                if (mode == 2)
+                    merge_min2(a, b, oa, ob);
+                else {
+                    a = oa < a ? oa : a;
+                    b = ob < b ? ob : b;
+                }
+            }
+            // every thread derives the same scalars; thread 0 publishes pi
+            unsigned long long key_sel;
+            double v0, vsel = 0.0, vnext = 0.0;
+            if (mode == 2) {
+                v0 = value_of_key(a, maximize);
+                vsel = v0;
+                vnext = value_of_key(b, maximize);
+                key_sel = a;
+            } else {
+                key_sel = ~a;
+                vsel = value_of_key(~a, maximize);
+                vnext = value_of_key(b, maximize);
+                v0 = selected >= 0 ? vsel : vnext; // only read when nothing is selected
+            }
+            double npi;
+            bool moves;
+            const double d =
+              affect_step(pr.delta, sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
+            if (tid == 0 && moves) {
+                s_pi[k] = npi; // all threads read pi[k] before the barrier above
+                if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
+                    sh->pi_changed = 1;
+            }
+            for (int i = tid; i < r_size; i += T) {
+                const unsigned long long key =
+                  key_of(__longlong_as_double((long long)key0[i]), maximize);
+                affect_element<FAM, SM>(L, r0, i, pown[i], selected >= 0 && key <= key_sel, d);
+            }
+            __syncthreads();
+            return;
+        }
+    }
+
+    // keys for the ordered paths (raw rows keep the value bits)
+    if (!raw) {
+        for (int i = tid; i < r_size; i += T)
+            L.key0[i] = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
+    }
+    if (tid == 0)
+        L.tab_dirty = 1;
+    __syncthreads();
+
+    bool slow = mode == 0;
+    if (!slow) {
+        row_select_sorted(L, k, r_size, n2, n_pre, kappa);
+        slow = L.sh->slow != 0;
+    }
+    if (slow) {
         if (tid == 0) {
             if (!raw)
                 row_select_exact(L, k, r_size, kappa, false, LessKey());
@@ -572,26 +906,14 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
         __syncthreads();
     }
 
-    // ---- D: x / P part of affect ------------------------------------------
+    // ---- D: x / P part of affect, by sorted position ------------------------
     {
-        const int selected = L.sh->selected;
+        const int sel = L.sh->selected;
         const double d = L.sh->d;
-        const bool all_out = selected < 0;
-        const bool all_in = !all_out && (selected + 1 >= r_size);
         const bool keep_tail = pb.tail_rows != 0;
-
         for (int p = tid; p < r_size; p += T) {
             const int id = L.sid[p];
-            const bool in = all_in || (!all_out && p <= selected);
-            const bool neg = pb.family != FAM_01 && pb.row_a[r0 + id] < 0;
-            const bool set = in != neg;
-            const int j = pb.row_col[r0 + id];
-            const double pv = L.pown[id];
-            L.P[L.opos[id]] = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
-            if (set)
-                atomicOr(&L.x[j >> 5], 1u << (j & 31));
-            else
-                atomicAnd(&L.x[j >> 5], ~(1u << (j & 31)));
+            affect_element<FAM, SM>(L, r0, id, pown[id], p <= sel, d);
             if (keep_tail)
                 L.Rv[p] = raw ? __longlong_as_double((long long)L.sk[p]) : value_of_key(L.sk[p], maximize);
         }
@@ -599,12 +921,10 @@ update_row(Lane& L, int k, double kappa, int push, double obj_amp)
     __syncthreads();
 }
 
-// Row activities and the violated list (compute_violated_constraints,
-// itm-common.hpp:102-115; infeasibility_local_compute_violated_constraints,
-// :893-914; local_compute_violated_constraints, :882-891).  mode: 0 = list of
-// violated rows into oR, 1 = (k, amount) pairs into mo, 2 = count only.
-__device__ int
-violated_scan(Lane& L, int mode)
+// Row activities from scratch (is_valid_constraint's sum, itm-common.hpp:76-89);
+// afterwards the updates keep them current.
+__device__ void
+activities_recompute(Lane& L)
 {
     const DevProblem& pb = *L.pb;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -623,19 +943,36 @@ violated_scan(Lane& L, int mode)
 #pragma unroll
         for (int o = 16; o; o >>= 1)
             v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-            const int lo = pb.bmin[k], hi = pb.bmax[k];
-            L.viol[k] = lo > v ? lo - v : (hi < v ? v - hi : 0);
-        }
+        if (lane == 0)
+            L.act[k] = v;
     }
     __syncthreads();
+    if (tid == 0)
+        L.alg_bytes += 4.0 * pb.nnz * (pb.family == FAM_01 ? 1.0 : 2.0) + pb.n / 8.0;
+}
+
+// The violated list (compute_violated_constraints, itm-common.hpp:102-115;
+// infeasibility_local_compute_violated_constraints, :893-914;
+// local_compute_violated_constraints, :882-891) from the row activities.
+// mode: 0 = list of violated rows into oR, 1 = (k, amount) pairs into mo,
+// 2 = count only.
+__device__ int
+violated_scan(Lane& L, int mode)
+{
+    const DevProblem& pb = *L.pb;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
 
     // ordered compaction by warp 0
     if (warp == 0) {
         int count = 0;
         for (int base = 0; base < pb.m; base += 32) {
             const int k = base + lane;
-            const int amount = k < pb.m ? L.viol[k] : 0;
+            int amount = 0;
+            if (k < pb.m) {
+                const int v = L.act[k], lo = pb.bmin[k], hi = pb.bmax[k];
+                amount = lo > v ? lo - v : (hi < v ? v - hi : 0);
+            }
             const unsigned mask = __ballot_sync(0xffffffffu, amount != 0);
             if (amount != 0) {
                 const int pos = count + __popc(mask & ((1u << lane) - 1u));
@@ -652,11 +989,10 @@ violated_scan(Lane& L, int mode)
                 L.sh->list_len = count;
             else if (mode == 1)
                 L.sh->tmp_i = count;
+            L.alg_bytes += 12.0 * pb.m;
         }
     }
     __syncthreads();
-    if (tid == 0)
-        L.alg_bytes += 4.0 * pb.nnz * (pb.family == FAM_01 ? 1.0 : 2.0) + 8.0 * pb.m + pb.n / 8.0;
     return L.sh->remaining;
 }
 
@@ -672,6 +1008,7 @@ __device__ void
 order_init(Lane& L, Lists& ls)
 {
     const int order = L.sh->order_state;
+    activities_recompute(L);
     if (order == ORDER_INFEASIBILITY_DECR || order == ORDER_INFEASIBILITY_INCR) {
         violated_scan(L, 1);
         ls.mo_len = L.sh->tmp_i;
@@ -683,6 +1020,39 @@ order_init(Lane& L, Lists& ls)
         violated_scan(L, 0);
         ls.oR_len = L.sh->list_len;
     }
+}
+
+// Single-thread preparation of the order list (the std::sort / std::shuffle
+// calls of compute_order::run, itm-common.hpp:700-780).  Kept out of line: its
+// stack and registers must not weigh on the update loop.
+__device__ __noinline__ void
+order_prepare(Lane& L, int order, int oR_len, int mo_len)
+{
+    uint32_t rng = L.sh->rng;
+    switch (order) {
+    case ORDER_RANDOM_SORTING:
+        seq_shuffle(Plain<int>{ L.oR }, 0, oR_len, rng);
+        break;
+    case ORDER_INFEASIBILITY_DECR:
+        seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessDecr());
+        break;
+    case ORDER_INFEASIBILITY_INCR:
+        seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessIncr());
+        break;
+    case ORDER_LAGRANGIAN_DECR:
+        seq_std_sort(Plain<int>{ L.oR }, oR_len, PiLessDecr{ L.pi });
+        break;
+    case ORDER_LAGRANGIAN_INCR:
+        seq_std_sort(Plain<int>{ L.oR }, oR_len, PiLessIncr{ L.pi });
+        break;
+    case ORDER_PI_SIGN_CHANGE:
+        seq_shuffle(Plain<int>{ L.oR }, 0, oR_len, rng);
+        L.sh->pi_changed = 0;
+        break;
+    default:
+        break;
+    }
+    L.sh->rng = rng;
 }
 
 // compute_order::run / push_and_run, itm-common.hpp:682-880
@@ -699,83 +1069,52 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
         __syncthreads();
     }
     const int order = L.sh->order_state;
-    L.sweeps += 1;
+    if (tid == 0) {
+        L.sweeps += 1;
+        L.sh->kk = __ddiv_rn(kappa, __dsub_rn(1.0, kappa));
+    }
+    __syncthreads();
 
-    switch (order) {
-    case ORDER_REVERSING:
-        L.updates += ls.oR_len;
-        for (int i = ls.oR_len - 1; i >= 0; --i)
-            update_row(L, L.oR[i], kappa, push, obj_amp);
-        violated_scan(L, 0);
-        ls.oR_len = L.sh->list_len;
-        return L.sh->remaining;
-    case ORDER_RANDOM_SORTING:
-        if (tid == 0) {
-            uint32_t rng = L.sh->rng;
-            seq_shuffle(Plain<int>{ L.oR }, 0, ls.oR_len, rng);
-            L.sh->rng = rng;
-        }
+    if (order >= ORDER_RANDOM_SORTING && order <= ORDER_PI_SIGN_CHANGE) {
+        if (tid == 0)
+            order_prepare(L, order, ls.oR_len, ls.mo_len);
         __syncthreads();
-        L.updates += ls.oR_len;
-        for (int i = 0; i < ls.oR_len; ++i)
-            update_row(L, L.oR[i], kappa, push, obj_amp);
-        violated_scan(L, 0);
-        ls.oR_len = L.sh->list_len;
-        return L.sh->remaining;
-    case ORDER_INFEASIBILITY_DECR:
-    case ORDER_INFEASIBILITY_INCR:
-        if (tid == 0) {
-            if (order == ORDER_INFEASIBILITY_DECR)
-                seq_std_sort(Plain<int2>{ L.mo }, ls.mo_len, PairLessDecr());
+    }
+
+    const bool pairs = order == ORDER_INFEASIBILITY_DECR || order == ORDER_INFEASIBILITY_INCR;
+    const int len = pairs ? ls.mo_len : ls.oR_len;
+    if (tid == 0)
+        L.updates += len;
+    for (int i = 0; i < len; ++i) {
+        int k;
+        if (pairs)
+            k = L.mo[i].x;
+        else
+            k = L.oR[order == ORDER_REVERSING ? len - 1 - i : i];
+        if (L.all_smem) {
+            if (L.pb->family == FAM_01)
+                update_row<FAM_01, true>(k, kappa, push, obj_amp);
             else
-                seq_std_sort(Plain<int2>{ L.mo }, ls.mo_len, PairLessIncr());
+                update_row<FAM_101, true>(k, kappa, push, obj_amp);
+        } else {
+            if (L.pb->family == FAM_01)
+                update_row<FAM_01, false>(k, kappa, push, obj_amp);
+            else
+                update_row<FAM_101, false>(k, kappa, push, obj_amp);
         }
-        __syncthreads();
-        L.updates += ls.mo_len;
-        for (int i = 0; i < ls.mo_len; ++i)
-            update_row(L, L.mo[i].x, kappa, push, obj_amp);
+    }
+
+    if (pairs) {
         violated_scan(L, 1);
         ls.mo_len = L.sh->tmp_i;
-        return L.sh->remaining;
-    case ORDER_LAGRANGIAN_DECR:
-    case ORDER_LAGRANGIAN_INCR:
-        if (tid == 0) {
-            if (order == ORDER_LAGRANGIAN_DECR)
-                seq_std_sort(Plain<int>{ L.oR }, ls.oR_len, PiLessDecr{ L.pi });
-            else
-                seq_std_sort(Plain<int>{ L.oR }, ls.oR_len, PiLessIncr{ L.pi });
-        }
-        __syncthreads();
-        L.updates += ls.oR_len;
-        for (int i = 0; i < ls.oR_len; ++i)
-            update_row(L, L.oR[i], kappa, push, obj_amp);
-        violated_scan(L, 0);
-        ls.oR_len = L.sh->list_len;
-        return L.sh->remaining;
-    case ORDER_PI_SIGN_CHANGE: {
-        if (tid == 0) {
-            uint32_t rng = L.sh->rng;
-            seq_shuffle(Plain<int>{ L.oR }, 0, ls.oR_len, rng);
-            L.sh->rng = rng;
-            L.sh->pi_changed = 0;
-        }
-        __syncthreads();
-        L.updates += ls.oR_len;
-        for (int i = 0; i < ls.oR_len; ++i)
-            update_row(L, L.oR[i], kappa, push, obj_amp);
-        const int remaining = violated_scan(L, 2);
+    } else if (order == ORDER_PI_SIGN_CHANGE) {
         // "if (!pi_changed && remaining == 0) return 0; return remaining;"
-        return remaining;
-    }
-    case ORDER_NONE:
-    default:
-        L.updates += ls.oR_len;
-        for (int i = 0; i < ls.oR_len; ++i)
-            update_row(L, L.oR[i], kappa, push, obj_amp);
+        violated_scan(L, 2);
+    } else {
         violated_scan(L, 0);
         ls.oR_len = L.sh->list_len;
-        return L.sh->remaining;
     }
+    return L.sh->remaining;
 }
 
 // default_cost_type::results, itm-common.hpp:1140-1147.  Result in
@@ -827,102 +1166,133 @@ struct SmemPlan
 {
     int pi_in_smem, x_in_smem, r_in_smem;
     int sort_cap;
+    int stage_cap;
 };
 
-// Bytes of the per-lane row scratch (key0, sk, sid, pown, opos), laid out the
+// Bytes of the per-lane row scratch (key0, sk, pown, sid), laid out the
 // same way in shared memory or in the batch's global scratch.
 __host__ __device__ inline size_t
-row_scratch_bytes(int max_row, int sort_cap)
+row_scratch_bytes(int max_row, int sort_cap, int stage_cap)
 {
     size_t n = 0;
+    n += sizeof(double) * 2 * (size_t)stage_cap;        // stage
     n += sizeof(unsigned long long) * (size_t)max_row;  // key0
     n += sizeof(unsigned long long) * (size_t)sort_cap; // sk
     n += sizeof(double) * (size_t)(max_row + 1);        // pown
     n += sizeof(int) * (size_t)sort_cap;                // sid
-    n += sizeof(int) * (size_t)(max_row + 1);           // opos
     return (n + 15) & ~size_t(15);
 }
 
-__device__ void
-lane_open(Lane& L, Lists& ls, const DevProblem& pb, const DevParams& pr,
-          const DevBatch& b, int lane_id, SmemPlan plan, unsigned char* smem)
+// Builds the lane's control block in shared memory (its fields are uniform
+// over the CTA) and stages pi, x, the row activities and R's leftover values.
+__device__ Lane&
+lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& b, int lane_id,
+          SmemPlan plan, unsigned char* smem)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     size_t off = 0;
 
-    L.pb = &pb;
-    L.pr = &pr;
-    L.sh = reinterpret_cast<Shared*>(smem);
-    off += (sizeof(Shared) + 15) & ~size_t(15);
-
-    L.P = b.P + (size_t)lane_id * pb.nnz;
-    L.ctl = b.ctl + lane_id;
-    L.oR = b.oR + (size_t)lane_id * b.order_cap;
-    L.mo = b.mo + (size_t)lane_id * b.order_cap;
-    L.sort_cap = plan.r_in_smem ? plan.sort_cap : 0;
+    Lane& L = *reinterpret_cast<Lane*>(smem);
+    off += kLaneBytes;
+    Shared* sh = reinterpret_cast<Shared*>(smem + off);
+    off += align16(sizeof(Shared));
 
     double* g_pi = b.pi + (size_t)lane_id * pb.m;
     uint32_t* g_x = b.x + (size_t)lane_id * pb.xw32;
     double* g_Rv = b.Rv + (size_t)lane_id * (pb.max_row + 2);
+    const int* g_act = b.act + (size_t)lane_id * pb.m;
+    LaneCtl* ctl = b.ctl + lane_id;
 
-    {
-        unsigned char* base;
-        if (plan.r_in_smem) {
-            base = smem + off;
-            off += row_scratch_bytes(pb.max_row, plan.sort_cap);
-        } else
-            base = b.g_scratch + (size_t)lane_id * row_scratch_bytes(pb.max_row, plan.sort_cap);
-        size_t o = 0;
-        L.key0 = reinterpret_cast<unsigned long long*>(base + o);
-        o += sizeof(unsigned long long) * (size_t)pb.max_row;
-        L.sk = reinterpret_cast<unsigned long long*>(base + o);
-        o += sizeof(unsigned long long) * (size_t)plan.sort_cap;
-        L.pown = reinterpret_cast<double*>(base + o);
-        o += sizeof(double) * (size_t)(pb.max_row + 1);
-        L.sid = reinterpret_cast<int*>(base + o);
-        o += sizeof(int) * (size_t)plan.sort_cap;
-        L.opos = reinterpret_cast<int*>(base + o);
-    }
-
+    unsigned char* scratch;
     if (plan.r_in_smem) {
-        L.Rv = reinterpret_cast<double*>(smem + off);
+        scratch = smem + off;
+        off += row_scratch_bytes(pb.max_row, plan.sort_cap, plan.stage_cap);
+    } else
+        scratch = b.g_scratch + (size_t)lane_id * row_scratch_bytes(pb.max_row, plan.sort_cap, plan.stage_cap);
+
+    double* s_Rv = g_Rv;
+    if (plan.r_in_smem) {
+        s_Rv = reinterpret_cast<double*>(smem + off);
         off += sizeof(double) * (size_t)(pb.max_row + 2);
         for (int i = tid; i < pb.max_row + 2; i += T)
-            L.Rv[i] = g_Rv[i];
-    } else
-        L.Rv = g_Rv;
+            s_Rv[i] = g_Rv[i];
+    }
 
+    double* s_pi = g_pi;
     if (plan.pi_in_smem) {
-        L.pi = reinterpret_cast<double*>(smem + off);
+        s_pi = reinterpret_cast<double*>(smem + off);
         off += sizeof(double) * (size_t)pb.m;
         for (int i = tid; i < pb.m; i += T)
-            L.pi[i] = g_pi[i];
-    } else
-        L.pi = g_pi;
+            s_pi[i] = g_pi[i];
+    }
 
-    L.viol = reinterpret_cast<int*>(smem + off);
+    int* s_act = reinterpret_cast<int*>(smem + off);
     off += sizeof(int) * (size_t)pb.m;
+    for (int i = tid; i < pb.m; i += T)
+        s_act[i] = g_act[i];
 
+    uint32_t* s_x = g_x;
     if (plan.x_in_smem) {
-        L.x = reinterpret_cast<uint32_t*>(smem + off);
+        s_x = reinterpret_cast<uint32_t*>(smem + off);
         off += sizeof(uint32_t) * (size_t)pb.xw32;
         for (int i = tid; i < pb.xw32; i += T)
-            L.x[i] = g_x[i];
-    } else
-        L.x = g_x;
+            s_x[i] = g_x[i];
+    }
 
     if (tid == 0) {
-        L.sh->rng = L.ctl->rng;
-        L.sh->order_state = L.ctl->order_state;
-        L.sh->pi_changed = 0;
-        L.sh->remaining = L.ctl->remaining;
+        L.pb = &pb;
+        L.pr = &pr;
+        L.sh = sh;
+        L.P = b.P + (size_t)lane_id * pb.nnz;
+        L.ctl = ctl;
+        L.oR = b.oR + (size_t)lane_id * b.order_cap;
+        L.mo = b.mo + (size_t)lane_id * b.order_cap;
+        L.sort_cap = plan.r_in_smem ? plan.sort_cap : 0;
+        L.all_smem = plan.r_in_smem && plan.pi_in_smem && plan.x_in_smem;
+        int bits = 1;
+        while ((1 << bits) < 2 * plan.sort_cap)
+            ++bits;
+        L.tab_bits = bits;
+        L.tab_gen = 0;
+        L.tab_dirty = 1;
+
+        size_t o = 0;
+        L.stage = reinterpret_cast<double*>(scratch + o);
+        L.stage_cap = plan.stage_cap;
+        o += sizeof(double) * 2 * (size_t)plan.stage_cap;
+        L.key0 = reinterpret_cast<unsigned long long*>(scratch + o);
+        o += sizeof(unsigned long long) * (size_t)pb.max_row;
+        L.sk = reinterpret_cast<unsigned long long*>(scratch + o);
+        o += sizeof(unsigned long long) * (size_t)plan.sort_cap;
+        L.pown = reinterpret_cast<double*>(scratch + o);
+        o += sizeof(double) * (size_t)(pb.max_row + 1);
+        L.sid = reinterpret_cast<int*>(scratch + o);
+
+        L.Rv = s_Rv;
+        L.pi = s_pi;
+        L.act = s_act;
+        L.x = s_x;
+        // offsets of the shared-memory views (meaningful when all_smem)
+        L.o_stage = (int)(reinterpret_cast<unsigned char*>(L.stage) - smem);
+        L.o_key0 = (int)(reinterpret_cast<unsigned char*>(L.key0) - smem);
+        L.o_sk = (int)(reinterpret_cast<unsigned char*>(L.sk) - smem);
+        L.o_pown = (int)(reinterpret_cast<unsigned char*>(L.pown) - smem);
+        L.o_pi = (int)(reinterpret_cast<unsigned char*>(s_pi) - smem);
+        L.o_act = (int)(reinterpret_cast<unsigned char*>(s_act) - smem);
+        L.o_x = (int)(reinterpret_cast<unsigned char*>(s_x) - smem);
+
+        sh->rng = ctl->rng;
+        sh->order_state = ctl->order_state;
+        sh->pi_changed = 0;
+        sh->remaining = ctl->remaining;
+        L.updates = 0;
+        L.sweeps = 0;
+        L.alg_bytes = 0.0;
     }
-    ls.oR_len = L.ctl->oR_len;
-    ls.mo_len = L.ctl->mo_len;
-    L.updates = 0;
-    L.sweeps = 0;
-    L.alg_bytes = 0.0;
+    ls.oR_len = ctl->oR_len;
+    ls.mo_len = ctl->mo_len;
     __syncthreads();
+    return L;
 }
 
 __device__ void
@@ -947,6 +1317,11 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
         for (int i = tid; i < pb.xw32; i += T)
             g_x[i] = L.x[i];
     }
+    {
+        int* g_act = b.act + (size_t)lane_id * pb.m;
+        for (int i = tid; i < pb.m; i += T)
+            g_act[i] = L.act[i];
+    }
     if (tid == 0) {
         L.ctl->rng = L.sh->rng;
         L.ctl->order_state = L.sh->order_state;
@@ -962,13 +1337,14 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-extern __shared__ __align__(16) unsigned char g_smem[];
 
 // Start of a run: engine, solver state, x (init policy bastert + Bernoulli
 // flips on the device, or a caller-provided x0), compute_order::init.
 // solver_functor::operator(), itm-solver-common.hpp:94-133.
-__global__ void
-k_begin(DevProblem pb, DevParams pr, DevBatch b, const uint32_t* seeds,
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_begin(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+        const __grid_constant__ DevBatch b, const uint32_t* seeds,
         const uint32_t* x0, const uint32_t* rng0, int reset_solver,
         int init_on_device, double init_random, const double* cost_orig,
         SmemPlan plan)
@@ -1053,47 +1429,49 @@ k_begin(DevProblem pb, DevParams pr, DevBatch b, const uint32_t* seeds,
     }
     __syncthreads();
 
-    Lane L;
     Lists ls;
-    lane_open(L, ls, pb, pr, b, lane_id, plan, g_smem);
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
     order_init(L, ls);
     lane_close(L, ls, pb, b, lane_id, plan);
 }
 
 // compute_order::init on a range of lanes (after bxg_batch_set_state).
-__global__ void
-k_order_init(DevProblem pb, DevParams pr, DevBatch b, int lane_first,
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_order_init(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+        const __grid_constant__ DevBatch b, int lane_first,
              SmemPlan plan)
 {
     const int lane_id = lane_first + blockIdx.x;
-    Lane L;
     Lists ls;
-    lane_open(L, ls, pb, pr, b, lane_id, plan, g_smem);
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
     order_init(L, ls);
     lane_close(L, ls, pb, b, lane_id, plan);
 }
 
 // One compute_order::run / push_and_run per lane.
-__global__ void
-k_sweep(DevProblem pb, DevParams pr, DevBatch b, int push, double obj_amp,
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_sweep(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+        const __grid_constant__ DevBatch b, int push, double obj_amp,
         SmemPlan plan)
 {
     const int lane_id = blockIdx.x;
-    Lane L;
     Lists ls;
-    lane_open(L, ls, pb, pr, b, lane_id, plan, g_smem);
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
     const double kappa = b.kappa[lane_id];
     order_run(L, ls, kappa, push, obj_amp);
     lane_close(L, ls, pb, b, lane_id, plan);
 }
 
-__global__ void
-k_objective(DevProblem pb, DevParams pr, DevBatch b, SmemPlan plan)
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_objective(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+        const __grid_constant__ DevBatch b, SmemPlan plan)
 {
     const int lane_id = blockIdx.x;
-    Lane L;
     Lists ls;
-    lane_open(L, ls, pb, pr, b, lane_id, plan, g_smem);
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
     const double v = objective(L);
     if (threadIdx.x == 0)
         L.ctl->objective = v;
@@ -1130,13 +1508,14 @@ store_best(Lane& L, const DevBatch& b, int lane_id, bool by_value, double value,
 
 // Whole solver_functor::operator() loop (itm-solver-common.hpp:135-225) for
 // one lane; the wall-clock time limit is handled by the host (limit sweeps).
-__global__ void
-k_solve(DevProblem pb, DevParams pr, DevBatch b, SmemPlan plan)
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+        const __grid_constant__ DevBatch b, SmemPlan plan)
 {
     const int lane_id = blockIdx.x;
-    Lane L;
     Lists ls;
-    lane_open(L, ls, pb, pr, b, lane_id, plan, g_smem);
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
 
     int status = 2;
     int m_best_remaining = INT_MAX; // m_best.remaining_constraints
@@ -1239,11 +1618,11 @@ pow2_at_least(int v)
 }
 
 static size_t
-smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap)
+smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, int stage_cap)
 {
-    size_t off = (sizeof(Shared) + 15) & ~size_t(15);
+    size_t off = kLaneBytes + align16(sizeof(Shared));
     if (r_in) {
-        off += row_scratch_bytes(pb.max_row, sort_cap);
+        off += row_scratch_bytes(pb.max_row, sort_cap, stage_cap);
         off += sizeof(double) * (size_t)(pb.max_row + 2);
     }
     if (pi_in)
@@ -1257,16 +1636,19 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap)
 size_t
 lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg)
 {
-    return row_scratch_bytes(pb.max_row, cfg.sort_cap);
+    return row_scratch_bytes(pb.max_row, cfg.sort_cap, cfg.stage_cap);
 }
 
 LaunchCfg
 plan_launch(const DevProblem& pb, int device)
 {
-    int max_optin = 0;
+    int max_optin = 0, per_sm = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     if (max_optin <= 0)
         max_optin = 48 * 1024;
+    if (per_sm <= 0)
+        per_sm = max_optin;
     const size_t budget = (size_t)max_optin - 1024;
 
     LaunchCfg cfg;
@@ -1274,27 +1656,50 @@ plan_launch(const DevProblem& pb, int device)
     cfg.pi_in_smem = 1;
     cfg.x_in_smem = 1;
     cfg.sort_cap = pow2_at_least(pb.max_row);
-    // drop the largest consumers first until the plan fits
-    auto fits = [&]() {
-        return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap) <= budget;
+    // staging buffer of the reduced-cost gather: at least one column, at most
+    // the longest row's entries
+    const int stage_min = pb.max_col > 256 ? pb.max_col : 256;
+    cfg.stage_cap = pb.max_S < stage_min ? stage_min : pb.max_S;
+    auto bytes = [&]() {
+        return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap,
+                          cfg.stage_cap);
     };
-    if (!fits())
+    {
+        // a smaller staging buffer (rows summed in chunks) when that lets
+        // eight lanes share an SM
+        const size_t target = (size_t)per_sm / 8 - 1024;
+        if (bytes() > target) {
+            cfg.stage_cap = stage_min;
+            const size_t fixed = bytes();
+            if (fixed < target) {
+                cfg.stage_cap += (int)((target - fixed) / 16);
+                if (cfg.stage_cap > pb.max_S)
+                    cfg.stage_cap = pb.max_S;
+            }
+        }
+    }
+    // drop the largest consumers first until the plan fits
+    if (bytes() > budget)
         cfg.x_in_smem = 0;
-    if (!fits()) {
+    if (bytes() > budget) {
         // rows too long for the shared-memory sort: scratch in global memory,
         // single-thread ordering only
         cfg.r_in_smem = 0;
         cfg.sort_cap = pb.max_row;
     }
-    if (!fits())
+    if (bytes() > budget)
         cfg.pi_in_smem = 0;
-    cfg.smem = smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap);
+    cfg.smem = bytes();
 
-    int t = 64;
-    while (t < pb.max_row && t < 1024)
-        t *= 2;
-    if (t < 128)
-        t = 128;
+    // enough threads for the row elements of the second gather stage, whole
+    // warps; BXG_THREADS overrides (experiments)
+    int t = ((pb.p95_row * 2 / 3 + 31) / 32) * 32;
+    if (const char* env = getenv("BXG_THREADS"))
+        t = (atoi(env) + 31) / 32 * 32;
+    if (t < 64)
+        t = 64;
+    if (t > 1024)
+        t = 1024;
     cfg.threads = t;
     return cfg;
 }
@@ -1304,7 +1709,32 @@ static void
 set_smem(K kernel, size_t smem)
 {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
 }
+
+// CTA size classes: each kernel is compiled once per class so that the
+// register budget follows the CTA size (small CTAs, several per SM, get more
+// registers per thread; 1024-thread CTAs are held to 64).
+#define BXG_LAUNCH_CLASS(KERNEL, MAXT, MINB, GRID, CFG, STREAM, ...)                         \
+    do {                                                                                    \
+        set_smem(KERNEL<MAXT, MINB>, (CFG).smem);                                           \
+        KERNEL<MAXT, MINB><<<(GRID), (CFG).threads, (CFG).smem, (STREAM)>>>(__VA_ARGS__);   \
+    } while (0)
+
+#define BXG_LAUNCH(KERNEL, GRID, CFG, STREAM, ...)                                          \
+    do {                                                                                    \
+        if ((CFG).threads <= 96)                                                            \
+            BXG_LAUNCH_CLASS(KERNEL, 96, 8, GRID, CFG, STREAM, __VA_ARGS__);                \
+        else if ((CFG).threads <= 128)                                                      \
+            BXG_LAUNCH_CLASS(KERNEL, 128, 6, GRID, CFG, STREAM, __VA_ARGS__);               \
+        else if ((CFG).threads <= 256)                                                      \
+            BXG_LAUNCH_CLASS(KERNEL, 256, 3, GRID, CFG, STREAM, __VA_ARGS__);               \
+        else if ((CFG).threads <= 512)                                                      \
+            BXG_LAUNCH_CLASS(KERNEL, 512, 1, GRID, CFG, STREAM, __VA_ARGS__);               \
+        else                                                                                \
+            BXG_LAUNCH_CLASS(KERNEL, 1024, 1, GRID, CFG, STREAM, __VA_ARGS__);              \
+    } while (0)
 
 void
 launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
@@ -1312,47 +1742,41 @@ launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
-    set_smem(k_begin, cfg.smem);
-    k_begin<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, d_seeds, d_x0, d_rng,
-                                                      reset_solver, init_on_device,
-                                                      init_random, d_cost_orig, plan);
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
+               init_on_device, init_random, d_cost_orig, plan);
 }
 
 void
 launch_order_init(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
-    set_smem(k_order_init, cfg.smem);
-    k_order_init<<<lane_count, cfg.threads, cfg.smem, s>>>(pb, pr, b, lane_first, plan);
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
 }
 
 void
 launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
-    set_smem(k_sweep, cfg.smem);
-    k_sweep<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, push, obj_amp, plan);
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
 }
 
 void
 launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
-    set_smem(k_solve, cfg.smem);
-    k_solve<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, plan);
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
 void
 launch_objective(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap };
-    set_smem(k_objective, cfg.smem);
-    k_objective<<<b.n_lanes, cfg.threads, cfg.smem, s>>>(pb, pr, b, plan);
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
 } // namespace bxg

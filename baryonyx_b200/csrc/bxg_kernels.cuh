@@ -36,12 +36,27 @@ enum
     Z_LINEAR
 };
 
+// What one constraint update needs to know about its row, in one 32-byte load.
+struct __align__(16) RowHdr
+{
+    int r0;     // first element (row_ptr[k])
+    int r_size; // number of elements
+    int g0;     // first expanded column entry (row_gptr[k])
+    int S;      // number of expanded column entries
+    int bmin, bmax;
+    int c_size; // elements with a negative factor (101)
+    float bytes; // algorithmic bytes of one update
+};
+
 // Read-only structure shared by all lanes.  P lives in CSC order (see
 // DESIGN.md): the gather for column j reads P[col_ptr[j] .. col_ptr[j+1])
 // contiguously, and the row's own entry is one of those.
 struct DevProblem
 {
     int m, n, nnz, max_row;
+    int p95_row; // 95th percentile of the row lengths
+    int max_col; // longest column
+    int max_S;   // most column entries met by one row (sum of its columns' lengths)
     int family, maximize;
     int xw32; // 32-bit words per x vector = 2 * (n/64 + 1)
     int n_obj;
@@ -50,13 +65,22 @@ struct DevProblem
     int tail_rows; // rows whose select_variables scan can read R[r_size]
     double cost_constant;
 
+    const RowHdr* row_hdr; // [m]
     const int* row_ptr;    // [m+1]
     const int* row_col;    // [nnz] column of each row element
     const int* row_cscpos; // [nnz] position of the element in CSC order
+    const int4* row_info;  // [nnz] {col_ptr[j], col_ptr[j+1], CSC position, j} of each row element
     const int* row_a;      // [nnz] factor (101/Z) or nullptr
     const int* col_ptr;    // [n+1]
     const int* csc_row;    // [nnz] row of each column entry, ascending
     const int* csc_a;      // [nnz] factor in CSC order (101/Z) or nullptr
+    const int* csc_rs;     // [nnz] row << 1 | (factor < 0), CSC order
+    // column entries of every row, expanded: for row k the entries of its
+    // columns one after the other, gp[row_gptr[k] + row_eptr[e] + t] =
+    // {CSC position, row << 1 | (factor < 0)} of entry t of row element e
+    const int2* gp;
+    const int* row_gptr; // [m+1]
+    const int* row_eptr; // [nnz] start of each row element inside its row's expansion
     const int* bmin;       // [m]
     const int* bmax;       // [m]
     const int* row_neg;    // [m] number of negative factors (101) or nullptr
@@ -113,6 +137,7 @@ struct DevBatch
     double* pi;      // [lanes][m]
     uint32_t* x;     // [lanes][xw32]
     uint32_t* bestx; // [lanes][xw32]
+    int* act;        // [lanes][m] row activities of x
     double* Rv;      // [lanes][max_row + 2] values left in the slots of the reference's R
     int* oR;         // [lanes][order_cap]
     int2* mo;        // [lanes][order_cap]
@@ -128,6 +153,7 @@ struct LaunchCfg
     size_t smem;
     int pi_in_smem, x_in_smem, r_in_smem;
     int sort_cap;
+    int stage_cap;
 };
 
 LaunchCfg plan_launch(const DevProblem& pb, int device);
