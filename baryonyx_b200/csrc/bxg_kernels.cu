@@ -253,6 +253,7 @@ affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0
 // the exact libstdc++ sort and shuffle permutations.  Used when the parallel
 // paths cannot decide the row (ties across the selection boundary, NaN, -0.0,
 // rows longer than the shared-memory sort).
+// @region row_select_exact
 template<typename Less>
 __device__ __noinline__ void
 row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
@@ -312,6 +313,7 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
     affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
 }
 
+// @region cta_bitonic_sort
 // Bitonic sort of sk[0..n2) (ascending) carrying sid, by the whole CTA.  n2
 // is a power of two.  Strides up to 32 stay inside the 64 elements one warp
 // owns, so only the wide strides need a CTA barrier.
@@ -347,6 +349,7 @@ cta_bitonic_sort(unsigned long long* sk, int* sid, int n2)
     __syncthreads();
 }
 
+// @region row_select_sorted
 // Parallel statement of calculator_sort + select_variables: the whole CTA
 // sorts the keys, the shuffle draws are accounted with the LCG jump-ahead
 // (they do not depend on the elements), one thread walks the window of
@@ -522,6 +525,7 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
     __syncthreads();
 }
 
+// @region affect_element
 // x / P part of affect (itm-common.hpp:404-463) for the element `id` of row k,
 // plus the row activities of the column when the bit flips.
 template<int FAM, bool SM>
@@ -555,6 +559,7 @@ affect_element(Lane& L, int r0, int id, double pv, bool in, double d)
     }
 }
 
+// @region helpers
 // 64-bit minimum over a warp with two 32-bit REDUX steps.
 __device__ __forceinline__ unsigned long long
 warp_min_u64(unsigned long long v)
@@ -578,6 +583,7 @@ merge_min2(unsigned long long& m1, unsigned long long& m2, unsigned long long o1
     m2 = hi < s2 ? hi : s2;
 }
 
+// @region update_row.head
 // One constraint update (the loop body of compute_update_row /
 // push_and_compute_update_row).  Called by all threads of the CTA.
 //
@@ -608,8 +614,8 @@ update_row(int k, double kappa, int push, double obj_amp)
     const double* __restrict__ cost = pr.cost;
     // shared-memory views (the Lane block itself always lives there)
     const int stage_cap = L.stage_cap;
-    double* const sp = view<SM>(L.stage, L.o_stage); // [stage_cap] P terms
-    double* const spi = sp + stage_cap;              // [stage_cap] pi terms
+    double* const sp = view<SM>(L.stage, L.o_stage);      // [stage_cap] P terms
+    int* const srs = reinterpret_cast<int*>(sp + stage_cap); // [stage_cap] row << 1 | negative
     double* const s_pi = view<SM>(L.pi, L.o_pi);
     unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
     double* const pown = view<SM>(L.pown, L.o_pown);
@@ -630,6 +636,7 @@ update_row(int k, double kappa, int push, double obj_amp)
     // the smallest stopping key (sb)
     unsigned long long ca = ~0ull, cb = ~0ull, sa = ~0ull, sb = ~0ull;
 
+// @region update_row.chunk
     for (int ia = 0; ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
         int ib = r_size;
@@ -648,6 +655,7 @@ update_row(int k, double kappa, int push, double obj_amp)
             fb = pb.row_eptr[r0 + ib];
         }
 
+// @region update_row.stage1
         // stage 1: entries
         for (int g = fa + tid; g < fb; g += 4 * T) {
             int2 e[4];
@@ -668,18 +676,16 @@ update_row(int k, double kappa, int push, double obj_amp)
                     double pv = p[u];
                     if (row == k)
                         pv = __dmul_rn(pv, theta);
-                    double a_pi = s_pi[row];
-                    if (FAM != FAM_01 && (e[u].y & 1)) {
+                    if (FAM != FAM_01 && (e[u].y & 1))
                         pv = -pv;
-                        a_pi = -a_pi;
-                    }
                     sp[gg - fa] = pv;
-                    spi[gg - fa] = a_pi;
+                    srs[gg - fa] = e[u].y;
                 }
             }
         }
         __syncthreads();
 
+// @region update_row.stage2
         // stage 2: elements
         for (int i = ia + tid; i < ib; i += T) {
             const int4 info = pb.row_info[r0 + i]; // c0, c1, own CSC position, column
@@ -688,7 +694,11 @@ update_row(int k, double kappa, int push, double obj_amp)
             const double cj = cost[info.w];
             double sum_pi = 0.0, sum_p = 0.0;
             for (int t = 0; t < len; ++t) {
-                sum_pi = __dadd_rn(sum_pi, spi[s0 + t]);
+                const int rs = srs[s0 + t];
+                double a_pi = s_pi[rs >> 1];
+                if (FAM != FAM_01 && (rs & 1))
+                    a_pi = -a_pi;
+                sum_pi = __dadd_rn(sum_pi, a_pi);
                 sum_p = __dadd_rn(sum_p, sp[s0 + t]);
             }
             double own = sp[s0 + (info.z - info.x)];
@@ -723,6 +733,7 @@ update_row(int k, double kappa, int push, double obj_amp)
             __syncthreads(); // the staging buffer is reused
     }
 
+// @region update_row.reduceA
     if (!is_eq) {
         counts = __reduce_add_sync(0xffffffffu, counts);
         if (ln == 0)
@@ -743,6 +754,7 @@ update_row(int k, double kappa, int push, double obj_amp)
 
     const int n2 = r_size <= 2 ? 2 : 1 << (32 - __clz(r_size - 1));
 
+// @region update_row.mode
     // ---- B: which elements are selected ------------------------------------
     // mode 0: exact single thread; 1: CTA sort; 2: two smallest; 3: boundary by sign
     int mode;
@@ -772,6 +784,7 @@ update_row(int k, double kappa, int push, double obj_amp)
     }
 
     if (mode >= 2) {
+// @region update_row.ties
         // No order is needed as long as all values differ: look for equal
         // values with a table of row positions hashed by key (32-bit entries
         // laid over sk, stamped with a generation so it is cleared rarely).
@@ -813,6 +826,7 @@ update_row(int k, double kappa, int push, double obj_amp)
             }
         }
 
+// @region update_row.candidates
         // candidates over the warp: mode 2 = the two smallest keys, mode 3 =
         // (largest non-stopping key, complemented; smallest stopping key)
         unsigned long long a, b;
@@ -847,6 +861,7 @@ update_row(int k, double kappa, int push, double obj_amp)
                     b = ob < b ? ob : b;
                 }
             }
+// @region update_row.scalars
             // every thread derives the same scalars; thread 0 publishes pi
             unsigned long long key_sel;
             double v0, vsel = 0.0, vnext = 0.0;
@@ -870,6 +885,7 @@ update_row(int k, double kappa, int push, double obj_amp)
                 if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
                     sh->pi_changed = 1;
             }
+// @region update_row.fastD
             for (int i = tid; i < r_size; i += T) {
                 const unsigned long long key =
                   key_of(__longlong_as_double((long long)key0[i]), maximize);
@@ -880,6 +896,7 @@ update_row(int k, double kappa, int push, double obj_amp)
         }
     }
 
+// @region update_row.ordered
     // keys for the ordered paths (raw rows keep the value bits)
     if (!raw) {
         for (int i = tid; i < r_size; i += T)
@@ -921,6 +938,7 @@ update_row(int k, double kappa, int push, double obj_amp)
     __syncthreads();
 }
 
+// @region activities
 // Row activities from scratch (is_valid_constraint's sum, itm-common.hpp:76-89);
 // afterwards the updates keep them current.
 __device__ void
@@ -951,6 +969,7 @@ activities_recompute(Lane& L)
         L.alg_bytes += 4.0 * pb.nnz * (pb.family == FAM_01 ? 1.0 : 2.0) + pb.n / 8.0;
 }
 
+// @region violated_scan
 // The violated list (compute_violated_constraints, itm-common.hpp:102-115;
 // infeasibility_local_compute_violated_constraints, :893-914;
 // local_compute_violated_constraints, :882-891) from the row activities.
@@ -1022,6 +1041,7 @@ order_init(Lane& L, Lists& ls)
     }
 }
 
+// @region order
 // Single-thread preparation of the order list (the std::sort / std::shuffle
 // calls of compute_order::run, itm-common.hpp:700-780).  Kept out of line: its
 // stack and registers must not weigh on the update loop.
@@ -1117,6 +1137,7 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     return L.sh->remaining;
 }
 
+// @region objective
 // default_cost_type::results, itm-common.hpp:1140-1147.  Result in
 // sh->tmp_d, valid for all threads after the call.
 __device__ double
@@ -1175,7 +1196,8 @@ __host__ __device__ inline size_t
 row_scratch_bytes(int max_row, int sort_cap, int stage_cap)
 {
     size_t n = 0;
-    n += sizeof(double) * 2 * (size_t)stage_cap;        // stage
+    n += (sizeof(double) + sizeof(int)) * (size_t)stage_cap; // stage: P terms, rows
+    n = (n + 15) & ~size_t(15);
     n += sizeof(unsigned long long) * (size_t)max_row;  // key0
     n += sizeof(unsigned long long) * (size_t)sort_cap; // sk
     n += sizeof(double) * (size_t)(max_row + 1);        // pown
@@ -1183,6 +1205,7 @@ row_scratch_bytes(int max_row, int sort_cap, int stage_cap)
     return (n + 15) & ~size_t(15);
 }
 
+// @region lane_open_close
 // Builds the lane's control block in shared memory (its fields are uniform
 // over the CTA) and stages pi, x, the row activities and R's leftover values.
 __device__ Lane&
@@ -1211,7 +1234,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         scratch = b.g_scratch + (size_t)lane_id * row_scratch_bytes(pb.max_row, plan.sort_cap, plan.stage_cap);
 
     double* s_Rv = g_Rv;
-    if (plan.r_in_smem) {
+    if (plan.r_in_smem && pb.tail_rows) {
         s_Rv = reinterpret_cast<double*>(smem + off);
         off += sizeof(double) * (size_t)(pb.max_row + 2);
         for (int i = tid; i < pb.max_row + 2; i += T)
@@ -1259,7 +1282,8 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         size_t o = 0;
         L.stage = reinterpret_cast<double*>(scratch + o);
         L.stage_cap = plan.stage_cap;
-        o += sizeof(double) * 2 * (size_t)plan.stage_cap;
+        o += (sizeof(double) + sizeof(int)) * (size_t)plan.stage_cap;
+        o = (o + 15) & ~size_t(15);
         L.key0 = reinterpret_cast<unsigned long long*>(scratch + o);
         o += sizeof(unsigned long long) * (size_t)pb.max_row;
         L.sk = reinterpret_cast<unsigned long long*>(scratch + o);
@@ -1302,7 +1326,7 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
     const int tid = threadIdx.x, T = blockDim.x;
     __syncthreads();
 
-    if (plan.r_in_smem) {
+    if (plan.r_in_smem && pb.tail_rows) {
         double* g_Rv = b.Rv + (size_t)lane_id * (pb.max_row + 2);
         for (int i = tid; i < pb.max_row + 2; i += T)
             g_Rv[i] = L.Rv[i];
@@ -1338,6 +1362,7 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
 // kernels
 // ---------------------------------------------------------------------------
 
+// @region kernels
 // Start of a run: engine, solver state, x (init policy bastert + Bernoulli
 // flips on the device, or a caller-provided x0), compute_order::init.
 // solver_functor::operator(), itm-solver-common.hpp:94-133.
@@ -1623,7 +1648,8 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, in
     size_t off = kLaneBytes + align16(sizeof(Shared));
     if (r_in) {
         off += row_scratch_bytes(pb.max_row, sort_cap, stage_cap);
-        off += sizeof(double) * (size_t)(pb.max_row + 2);
+        if (pb.tail_rows)
+            off += sizeof(double) * (size_t)(pb.max_row + 2);
     }
     if (pi_in)
         off += sizeof(double) * (size_t)pb.m;
@@ -1672,7 +1698,7 @@ plan_launch(const DevProblem& pb, int device)
             cfg.stage_cap = stage_min;
             const size_t fixed = bytes();
             if (fixed < target) {
-                cfg.stage_cap += (int)((target - fixed) / 16);
+                cfg.stage_cap += (int)((target - fixed) / 12);
                 if (cfg.stage_cap > pb.max_S)
                     cfg.stage_cap = pb.max_S;
             }
@@ -1693,7 +1719,7 @@ plan_launch(const DevProblem& pb, int device)
 
     // enough threads for the row elements of the second gather stage, whole
     // warps; BXG_THREADS overrides (experiments)
-    int t = ((pb.p95_row * 2 / 3 + 31) / 32) * 32;
+    int t = ((pb.p95_row / 2 + 31) / 32) * 32;
     if (const char* env = getenv("BXG_THREADS"))
         t = (atoi(env) + 31) / 32 * 32;
     if (t < 64)

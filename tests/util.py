@@ -69,3 +69,44 @@ def lockstep(run_a, run_b, m, p, sweeps, pushes_every=0, order_pairs=False):
         if kappa > p.kappa_max:
             return s + 1
     return sweeps
+
+
+# ---------------------------------------------------------------------------
+# golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py
+# from the compiled reference)
+# ---------------------------------------------------------------------------
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    """-> (instance dict, clamped Params, npz)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    m, n, ptype, maximize = [int(v) for v in z["inst_scalars"]]
+    inst = {
+        "m": m, "n": n, "problem_type": ptype, "maximize": maximize,
+        "cost_constant": float(z["inst_cost_constant"]),
+    }
+    for k in ("row_ptr", "col", "factor", "cmin", "cmax", "obj_var", "obj_factor"):
+        inst[k] = z["inst_" + k]
+    p = po.Params()
+    for (fname, ftype), v in zip(po.Params._fields_, z["params"]):
+        setattr(p, fname, float(v) if "double" in ftype.__name__ else int(v))
+    return inst, p, z
+
+
+def golden_kappa_schedule(z, p, m, lane):
+    """Yields (sweep index, push flag, kappa) following the recorded remaining
+    counts, exactly as make_golden.trajectory drove the reference."""
+    kappa = p.kappa_min
+    pushes_every = int(z["pushes_every"])
+    rem = z[f"rem_{lane}"]
+    for s in range(int(z["sweeps"])):
+        push = 1 if (pushes_every and s % pushes_every == pushes_every - 1) else 0
+        yield s, push, kappa
+        if s > p.w:
+            kappa += p.kappa_step * (int(rem[s + 1]) / m) ** p.alpha
+        kappa = min(kappa, 0.999)
