@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbaryonyx_b200.so")
 SOURCES = ["bxg_api.cu", "bxg_kernels.cu"]
-HEADERS = ["bxg_device.cuh", "bxg_kernels.cuh", os.path.join("..", "..", "include", "bxg.h")]
+HEADERS = ["bxg_device.cuh", "bxg_kernels.cuh", "bxg_zsolver.cuh", os.path.join("..", "..", "include", "bxg.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

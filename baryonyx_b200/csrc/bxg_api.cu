@@ -99,6 +99,8 @@ struct bxg_problem
     std::vector<int> row_gptr, row_eptr;
     int max_col = 0, max_S = 0;
     std::vector<int> cmin, cmax, bmin, bmax, row_neg, ztype;
+    std::vector<int> ex_start, ex_count, ex_flat; // (Z) exhaustive rows: pattern masks
+    int max_zrow = 0;
     std::vector<float> row_bytes;
     std::vector<int> obj_var;
     std::vector<double> obj_factor;
@@ -107,7 +109,8 @@ struct bxg_problem
     int tail_rows = 0; // rows that can read R[r_size]
 
     DevBuf<int> d_row_ptr, d_row_col, d_row_a, d_row_cscpos, d_col_ptr, d_csc_row,
-      d_csc_a, d_csc_rs, d_bmin, d_bmax, d_row_neg, d_ztype, d_obj_var;
+      d_csc_a, d_csc_rs, d_bmin, d_bmax, d_row_neg, d_ztype, d_obj_var, d_ex_start, d_ex_count,
+      d_ex_flat;
     DevBuf<int4> d_row_info;
     DevBuf<int2> d_gp;
     DevBuf<RowHdr> d_row_hdr;
@@ -129,7 +132,7 @@ struct bxg_batch
     std::vector<double> norm_cost, powtab;
 
     DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_Rv;
-    DevBuf<unsigned char> d_scratch;
+    DevBuf<unsigned char> d_scratch, d_zscratch;
     DevBuf<uint32_t> d_x, d_bestx, d_seeds, d_x0, d_rng0;
     DevBuf<int> d_oR, d_act;
     DevBuf<int2> d_mo;
@@ -486,6 +489,8 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     pb->bmax.resize(m);
     pb->row_neg.assign(m, 0);
     pb->ztype.assign(m, Z_LINEAR);
+    pb->ex_start.assign(m, 0);
+    pb->ex_count.assign(m, 0);
     pb->row_bytes.resize(m);
     for (int k = 0; k != m; ++k) {
         const int len = row_ptr[k + 1] - row_ptr[k];
@@ -526,9 +531,75 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
                 pb->bmax[k] = std::min(len - neg, cmax[k]);
             }
             break;
-        default:
-            return fail(BXG_E_UNSUPPORTED,
-                        "the Z-coefficient solver is not part of this build yet");
+        default: {
+            // itm-solver-inequalities-Z.cpp:125-183
+            int zt = Z_LINEAR;
+            for (int i = 0; i != len; ++i)
+                if (f[i] < -1 || f[i] > 1)
+                    zt = Z_BRANCH_AND_BOUND;
+            if (zt == Z_BRANCH_AND_BOUND && len < 10)
+                zt = Z_EXHAUSTIVE;
+
+            if (cmin[k] == cmax[k]) {
+                pb->bmin[k] = cmin[k];
+                pb->bmax[k] = cmax[k];
+            } else {
+                if (lower >= cmin[k] || upper <= cmax[k]) {
+                    if (zt == Z_BRANCH_AND_BOUND)
+                        zt = Z_UNCONSTRAINED_BRANCH_AND_BOUND;
+                    else if (zt == Z_EXHAUSTIVE)
+                        zt = Z_UNCONSTRAINED_EXHAUSTIVE;
+                }
+                pb->bmin[k] = std::max(lower, cmin[k]);
+                pb->bmax[k] = std::min(upper, cmax[k]);
+            }
+            pb->ztype[k] = zt;
+
+            if (zt != Z_LINEAR) {
+                pb->max_zrow = std::max(pb->max_zrow, len);
+                // a sub-solver may answer r_size, and local_affect then reads
+                // the slot one past the row
+                pb->tail_rows++;
+            }
+            if (zt == Z_EXHAUSTIVE || zt == Z_UNCONSTRAINED_EXHAUSTIVE) {
+                // exhaustive_solver::build_constraints, exhaustive-solver.hpp:
+                // 111-167: a binary counter over the row's elements, the last
+                // element being the lowest digit.  The states met WHILE a
+                // carry propagates are tested too, so a pattern can be listed
+                // more than once; the list is kept as the reference builds it
+                // because its order breaks ties between patterns.
+                pb->ex_start[k] = static_cast<int>(pb->ex_flat.size());
+                std::vector<int> digit(len, 0);
+                digit[len - 1] = 1;
+                bool end = false;
+                while (!end) {
+                    int i = len - 1;
+                    for (;;) {
+                        int sum = 0, mask = 0;
+                        for (int jx = 0; jx != len; ++jx)
+                            if (digit[jx]) {
+                                sum += f[jx];
+                                mask |= 1 << jx;
+                            }
+                        if (pb->bmin[k] <= sum && sum <= pb->bmax[k])
+                            pb->ex_flat.push_back(mask);
+                        if (++digit[i] > 1) {
+                            digit[i] = 0;
+                            if (i == 0) {
+                                end = true;
+                                break;
+                            }
+                            --i;
+                        } else
+                            break;
+                    }
+                }
+                pb->ex_count[k] = static_cast<int>(pb->ex_flat.size()) - pb->ex_start[k];
+                if (pb->ex_count[k] == 0)
+                    return fail(BXG_E_UNREALISABLE,
+                                "constraint without any feasible assignment (exhaustive row)");
+            }
+        } break;
         }
 
         if (pb->bmin[k] > pb->bmax[k])
@@ -611,6 +682,11 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     CUDA_TRY(pb->d_row_neg.upload(pb->row_neg));
     CUDA_TRY(pb->d_row_bytes.upload(pb->row_bytes));
     CUDA_TRY(pb->d_ztype.upload(pb->ztype));
+    if (pb->family == FAM_Z) {
+        CUDA_TRY(pb->d_ex_start.upload(pb->ex_start));
+        CUDA_TRY(pb->d_ex_count.upload(pb->ex_count));
+        CUDA_TRY(pb->d_ex_flat.upload(pb->ex_flat));
+    }
     CUDA_TRY(pb->d_obj_var.upload(pb->obj_var));
     CUDA_TRY(pb->d_obj_factor.upload(pb->obj_factor));
     CUDA_TRY(pb->d_cost.upload(pb->cost));
@@ -649,9 +725,10 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.row_neg = pb->d_row_neg.p;
     d.row_bytes = pb->d_row_bytes.p;
     d.ztype = pb->d_ztype.p;
-    d.ex_start = nullptr;
-    d.ex_count = nullptr;
-    d.ex_flat = nullptr;
+    d.max_zrow = pb->max_zrow;
+    d.ex_start = pb->family == FAM_Z ? pb->d_ex_start.p : nullptr;
+    d.ex_count = pb->family == FAM_Z ? pb->d_ex_count.p : nullptr;
+    d.ex_flat = pb->family == FAM_Z ? pb->d_ex_flat.p : nullptr;
     d.obj_var = pb->d_obj_var.p;
     d.obj_factor = pb->d_obj_factor.p;
 
@@ -789,6 +866,12 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     b->cfg = plan_launch(pb->dev, pb->device);
     if (!b->cfg.r_in_smem)
         CUDA_TRY(b->d_scratch.alloc(L * lane_scratch_bytes(pb->dev, b->cfg)));
+    const size_t zbytes = z_scratch_bytes(pb->max_zrow);
+    if (zbytes) {
+        if (zbytes > (size_t{ 1 } << 26))
+            return fail(BXG_E_MEMORY, "branch-and-bound row too long for the device scratch");
+        CUDA_TRY(b->d_zscratch.alloc(L * zbytes));
+    }
 
     DevBatch& d = b->dev;
     d.n_lanes = n_lanes;
@@ -804,6 +887,8 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     d.ctl = b->d_ctl.p;
     d.kappa = b->d_kappa.p;
     d.g_scratch = b->cfg.r_in_smem ? nullptr : b->d_scratch.p;
+    d.z_scratch = zbytes ? b->d_zscratch.p : nullptr;
+    d.z_bytes = zbytes;
 
     refresh_params(b.get());
 

@@ -18,6 +18,7 @@
 //    (the reference reads it, itm-solver-inequalities-01.cpp:198-203).
 #include "bxg_device.cuh"
 #include "bxg_kernels.cuh"
+#include "bxg_zsolver.cuh"
 
 #include <climits>
 #include <math_constants.h>
@@ -74,6 +75,7 @@ struct Lane
     int2* mo;
     LaneCtl* ctl;
     Shared* sh;
+    unsigned char* zs; // (Z) scratch of the sub-solvers, global memory
     int all_smem;  // pi, x and the row scratch are all in shared memory
     // byte offsets into g_smem of the views that live there (all_smem)
     int o_stage, o_key0, o_sk, o_pown, o_pi, o_act, o_x;
@@ -938,6 +940,235 @@ update_row(int k, double kappa, int push, double obj_amp)
     __syncthreads();
 }
 
+// @region update_row_z
+// select_variables / select_variables_101 of the Z solver (identical bodies,
+// itm-solver-inequalities-Z.cpp:308-344): the longest prefix of the ordered
+// row whose factor sum is inside the bounds, stopping at the first value of
+// the wrong sign once one prefix fits.  -2 when no prefix fits.  (The
+// reference's last trip reads R[r_size]; it cannot change the result.)
+__device__ inline int
+z_select_prefix(const ZRow& R, int r_size, int bkmin, int bkmax, bool maximize)
+{
+    int sum = 0;
+    int best = -2;
+    for (int i = -1; i < r_size; ++i) {
+        if (bkmin <= sum && sum <= bkmax)
+            best = i;
+        if (i + 1 == r_size)
+            break;
+        if (best != -2) {
+            const double v = R.value(i + 1);
+            if (maximize ? v < 0 : v > 0)
+                break;
+        }
+        sum += R.factor(i + 1);
+    }
+    return best;
+}
+
+// One constraint update of the Z solver (compute_update_row /
+// push_and_compute_update_row, itm-solver-inequalities-Z.cpp:441-564).
+//  A. decrease_preference + compute_reduced_costs (:242-293): one thread per
+//     row element walks its column in CSC order with the reference's single
+//     accumulator sum |a| (pi + P).
+//  B. calculator_sort where the row type asks for it: the CTA's bitonic
+//     network when all values differ (the order is then unique), else the
+//     exact libstdc++ sort + shuffles by one thread; then the row's selection
+//     rule (prefix, exhaustive, branch and bound) by one thread.
+//  C. local_affect (:346-439), one thread per element: P +- d, the x bit, and
+//     the "repair" step that re-reads the element's column and pushes P past
+//     zero.  Elements of a row sit in different columns, so they are
+//     independent once pi_k is known.
+template<bool SM>
+__device__ __noinline__ void
+update_row_z(int k, double kappa, int push, double obj_amp)
+{
+    Lane& L = the_lane();
+    const DevProblem& pb = *L.pb;
+    const DevParams& pr = *L.pr;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const RowHdr hdr = pb.row_hdr[k];
+    const int r0 = hdr.r0;
+    const int r_size = hdr.r_size;
+    const double theta = pr.theta;
+    const bool maximize = pb.maximize != 0;
+    const double* __restrict__ cost = pr.cost;
+    double* const s_pi = view<SM>(L.pi, L.o_pi);
+    unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
+    unsigned long long* const sk = view<SM>(L.sk, L.o_sk);
+    double* const pown = view<SM>(L.pown, L.o_pown);
+    int* const sid = L.sid;
+    double* const gP = L.P;
+    Shared* const sh = the_shared();
+    const int zt = pb.ztype[k];
+
+    if (tid == 0)
+        L.alg_bytes += hdr.bytes;
+
+    // ---- A ---------------------------------------------------------------
+    int odd = 0;
+    for (int i = tid; i < r_size; i += T) {
+        const int4 info = pb.row_info[r0 + i]; // c0, c1, own CSC position, column
+        double sum = 0.0, own = 0.0;
+        for (int t = info.x; t < info.y; ++t) {
+            const int a = pb.csc_a[t];
+            double p = gP[t];
+            if (t == info.z) {
+                p = __dmul_rn(p, theta);
+                own = p;
+            }
+            sum = __dadd_rn(sum, __dmul_rn((double)(a < 0 ? -a : a),
+                                           __dadd_rn(s_pi[pb.csc_rs[t] >> 1], p)));
+        }
+        const double cj = cost[info.w];
+        double v = __dsub_rn(cj, sum);
+        if (push)
+            v = __dadd_rn(v, __dmul_rn(obj_amp, cj));
+        if (v != v || (v == 0.0 && __double_as_longlong(v) < 0))
+            odd = 1;
+        key0[i] = (unsigned long long)__double_as_longlong(v);
+        pown[i] = own;
+    }
+    const bool raw = __syncthreads_or(odd) != 0;
+
+    // ---- B ---------------------------------------------------------------
+    const bool ordered = zt != Z_EXHAUSTIVE && r_size > 1;
+    bool sorted = false;
+    if (ordered && !raw && r_size > 32) {
+        const int n2 = 1 << (32 - __clz(r_size - 1));
+        if (n2 <= L.sort_cap) {
+            for (int i = tid; i < n2; i += T) {
+                sk[i] = i < r_size ? key_of(__longlong_as_double((long long)key0[i]), maximize)
+                                   : ~0ull;
+                sid[i] = i;
+            }
+            __syncthreads();
+            cta_bitonic_sort(sk, sid, n2);
+            int tie = 0;
+            for (int p = tid + 1; p < r_size; p += T)
+                tie |= (sk[p] == sk[p - 1]);
+            sorted = __syncthreads_or(tie) == 0;
+            if (sorted) {
+                for (int p = tid; p < r_size; p += T)
+                    sk[p] = (unsigned long long)__double_as_longlong(value_of_key(sk[p], maximize));
+            }
+            __syncthreads();
+        }
+    }
+    if (!sorted) {
+        for (int i = tid; i < r_size; i += T) {
+            sk[i] = key0[i];
+            sid[i] = i;
+        }
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        const ZRow R{ L.sk, L.sid, pb.row_a + r0 };
+        uint32_t rng = sh->rng;
+        if (ordered && !sorted) {
+            // calculator_sort, itm-common.hpp:134-148
+            const Pairs a{ L.sk, L.sid };
+            if (maximize)
+                seq_std_sort(a, r_size, LessRawMax());
+            else
+                seq_std_sort(a, r_size, LessRawMin());
+            int ret = 0;
+            int i = 1;
+            for (; i != r_size; ++i) {
+                if (R.value(ret) != R.value(i)) {
+                    seq_shuffle(a, ret, i - ret, rng);
+                    ret = i;
+                }
+            }
+            seq_shuffle(a, ret, i - ret, rng);
+            sh->rng = rng;
+        }
+
+        const int bkmin = hdr.bmin, bkmax = hdr.bmax;
+        int selected;
+        if (zt == Z_LINEAR)
+            selected = z_select_prefix(R, r_size, bkmin, bkmax, maximize);
+        else {
+            const ZWork w(L.zs, pb.max_zrow);
+            selected = -2;
+            if (zt == Z_UNCONSTRAINED_BRANCH_AND_BOUND || zt == Z_UNCONSTRAINED_EXHAUSTIVE)
+                selected = z_select_prefix(R, r_size, bkmin, bkmax, maximize);
+            if (selected == -2) {
+                if (zt == Z_BRANCH_AND_BOUND || zt == Z_UNCONSTRAINED_BRANCH_AND_BOUND)
+                    selected = z_bb_solve(w, R, r_size, maximize, bkmin, bkmax);
+                else
+                    selected = z_ex_solve(w, R, r_size, maximize, pb.ex_flat + pb.ex_start[k],
+                                          pb.ex_count[k]);
+            }
+        }
+
+        // scalars of local_affect: pi_k moves in all three cases
+        const double old_pi = L.pi[k];
+        double npi;
+        if (selected < 0)
+            npi = __dadd_rn(old_pi, __dmul_rn(R.value(0), 0.5));
+        else if (selected + 1 >= r_size) {
+            // a sub-solver may answer r_size: the reference then reads the
+            // slot one past the row (what an earlier, longer row left there)
+            const double vs = selected < r_size ? R.value(selected) : L.Rv[selected];
+            npi = __dadd_rn(old_pi, __dmul_rn(vs, 1.5));
+        } else
+            npi = __dadd_rn(old_pi, __dmul_rn(__dadd_rn(R.value(selected), R.value(selected + 1)), 0.5));
+        L.pi[k] = npi;
+        if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
+            sh->pi_changed = 1;
+        sh->selected = selected;
+        sh->d = __dadd_rn(sh->kk, pr.delta);
+    }
+    __syncthreads();
+
+    // ---- C ---------------------------------------------------------------
+    {
+        const int sel = sh->selected;
+        const double d = sh->d;
+        const bool keep_tail = pb.tail_rows != 0;
+        uint32_t* const x = view<SM>(L.x, L.o_x);
+        int* const act = view<true>(L.act, L.o_act);
+        for (int p = tid; p < r_size; p += T) {
+            const int id = sid[p];
+            const int4 info = pb.row_info[r0 + id];
+            const bool set = sel >= 0 && (sel + 1 >= r_size || p <= sel);
+            double pv = pown[id];
+            pv = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
+
+            const int j = info.w;
+            const uint32_t bit = 1u << (j & 31);
+            const bool flips = ((x[j >> 5] & bit) != 0) != set;
+            if (flips)
+                atomicXor(&x[j >> 5], bit);
+
+            // local_compute_reduced_cost, :295-306, with the new pi_k and P
+            double sum = 0.0;
+            for (int t = info.x; t < info.y; ++t) {
+                const int a = pb.csc_a[t];
+                const double pt = t == info.z ? pv : gP[t];
+                sum = __dadd_rn(sum, __dmul_rn((double)(a < 0 ? -a : a),
+                                               __dadd_rn(s_pi[pb.csc_rs[t] >> 1], pt)));
+                if (flips)
+                    atomicAdd(&act[pb.csc_rs[t] >> 1], set ? a : -a);
+            }
+            const double repair = __dsub_rn(cost[j], sum);
+            if (set) {
+                if (repair >= 0)
+                    pv = __dadd_rn(__dsub_rn(pv, repair), d);
+            } else if (repair <= 0)
+                pv = __dsub_rn(__dadd_rn(pv, repair), d);
+            gP[info.z] = pv;
+
+            if (keep_tail)
+                L.Rv[p] = __longlong_as_double((long long)sk[p]);
+        }
+    }
+    __syncthreads();
+}
+
+
 // @region activities
 // Row activities from scratch (is_valid_constraint's sum, itm-common.hpp:76-89);
 // afterwards the updates keep them current.
@@ -1114,13 +1345,17 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
         if (L.all_smem) {
             if (L.pb->family == FAM_01)
                 update_row<FAM_01, true>(k, kappa, push, obj_amp);
-            else
+            else if (L.pb->family == FAM_101)
                 update_row<FAM_101, true>(k, kappa, push, obj_amp);
+            else
+                update_row_z<true>(k, kappa, push, obj_amp);
         } else {
             if (L.pb->family == FAM_01)
                 update_row<FAM_01, false>(k, kappa, push, obj_amp);
-            else
+            else if (L.pb->family == FAM_101)
                 update_row<FAM_101, false>(k, kappa, push, obj_amp);
+            else
+                update_row_z<false>(k, kappa, push, obj_amp);
         }
     }
 
@@ -1268,6 +1503,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.sh = sh;
         L.P = b.P + (size_t)lane_id * pb.nnz;
         L.ctl = ctl;
+        L.zs = b.z_scratch ? b.z_scratch + (size_t)lane_id * b.z_bytes : nullptr;
         L.oR = b.oR + (size_t)lane_id * b.order_cap;
         L.mo = b.mo + (size_t)lane_id * b.order_cap;
         L.sort_cap = plan.r_in_smem ? plan.sort_cap : 0;
@@ -1657,6 +1893,15 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, in
     if (x_in)
         off += sizeof(uint32_t) * (size_t)pb.xw32;
     return off + 16;
+}
+
+size_t
+z_scratch_bytes(int max_zrow)
+{
+    if (max_zrow <= 0)
+        return 0;
+    const size_t n = z_items_bytes(max_zrow) + z_nodes_bytes(max_zrow) + z_pool_bytes(max_zrow);
+    return (n + 15) & ~size_t(15);
 }
 
 size_t

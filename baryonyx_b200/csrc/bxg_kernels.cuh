@@ -63,6 +63,7 @@ struct DevProblem
     int obj_any_order; // objective sums are exact in any order
     int need_z;
     int tail_rows; // rows whose select_variables scan can read R[r_size]
+    int max_zrow;  // (Z) longest row handled by branch-and-bound / exhaustive
     double cost_constant;
 
     const RowHdr* row_hdr; // [m]
@@ -88,7 +89,7 @@ struct DevProblem
     const int* ztype;      // [m] (Z) or nullptr
     const int* ex_start;   // [m] offset into ex_flat (Z)
     const int* ex_count;   // [m] number of patterns (Z)
-    const int* ex_flat;    // patterns (Z)
+    const int* ex_flat;    // feasible 0/1 patterns of the row as bit masks (Z)
     const int* obj_var;    // [n_obj]
     const double* obj_factor; // [n_obj]
 };
@@ -145,6 +146,9 @@ struct DevBatch
     double* kappa;   // [lanes] input of bxg_batch_sweep
     // row scratch when it does not fit the shared-memory budget, else nullptr
     unsigned char* g_scratch; // [lanes][lane_scratch_bytes]
+    // (Z) items / node stack / subvector pool of the sub-solvers
+    unsigned char* z_scratch; // [lanes][z_bytes]
+    size_t z_bytes;
 };
 
 struct LaunchCfg
@@ -158,6 +162,7 @@ struct LaunchCfg
 
 LaunchCfg plan_launch(const DevProblem& pb, int device);
 size_t lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg);
+size_t z_scratch_bytes(int max_zrow);
 
 void launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   const uint32_t* d_seeds, const uint32_t* d_x0,

@@ -134,7 +134,7 @@ def csplib022(m=30, n=50000, lo=5, hi=15, neg_frac=0.2, seed=3, name="csplib022-
     return _finish(m, n, rows, factors, b, b, costs, name=name)
 
 
-def telebus(m=1500, n=7000, seed=4, name="telebus-shaped"):
+def telebus(m=1500, n=7000, seed=4, linear_hi=25, name="telebus-shaped"):
     """C4: general integer coefficients (inequalities_Z).  Most rows are 0/1 or
     +-1 (linear sub-solver); about 10% carry a coefficient with |f| >= 2 drawn
     from U{-3..9}\\{0}: half of those short (< 10 elements, exhaustive), half
@@ -150,7 +150,7 @@ def telebus(m=1500, n=7000, seed=4, name="telebus-shaped"):
             size = int(rng.randint(10, 17))
             zrow = True
         else:
-            size = int(rng.randint(3, 25))
+            size = int(rng.randint(3, linear_hi))
             zrow = False
         cols = sorted(rng.choice(n, size=size, replace=False).tolist())
         if zrow:

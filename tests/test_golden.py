@@ -11,7 +11,6 @@ from oracle import pyoracle as po
 from tests import util
 
 NAMES = util.golden_names()
-ENGINE_FAMILIES = (0, 1, 3, 4)  # problem types the CUDA engine implements (01 and 101)
 
 
 def test_fixtures_present():
@@ -55,8 +54,6 @@ def test_engine_reproduces_reference_trajectory(name):
     from baryonyx_b200 import capi
 
     inst, p, z = util.load_golden(name)
-    if inst["problem_type"] not in ENGINE_FAMILIES:
-        pytest.skip("Z family: not in the CUDA engine yet")
     q = capi.Params()
     C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
     seeds = [int(s) for s in z["seeds"]]

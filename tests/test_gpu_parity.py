@@ -73,7 +73,7 @@ def lockstep_engine(inst, p, seeds, sweeps, pushes_every=0, tail=0.0):
     bt.close(), pb.close(), op.close()
 
 
-@pytest.mark.parametrize("family", ["01", "101"])
+@pytest.mark.parametrize("family", ["01", "101", "Z"])
 @pytest.mark.parametrize("equality", [False, True])
 @pytest.mark.parametrize("maximize", [False, True])
 def test_sweeps_small(family, equality, maximize):
@@ -86,7 +86,7 @@ def test_sweeps_small(family, equality, maximize):
 @pytest.mark.parametrize("order", ["none", "reversing", "random-sorting", "infeasibility-decr",
                                    "infeasibility-incr", "lagrangian-decr", "lagrangian-incr",
                                    "pi-sign-change", "cycle"])
-@pytest.mark.parametrize("family", ["01", "101"])
+@pytest.mark.parametrize("family", ["01", "101", "Z"])
 def test_sweeps_orders(order, family):
     if order in ("pi-sign-change", "cycle"):
         inst = synth.small_mixed(m=30, n=20, seed=5, family=family, cost_hi=3, density=0.3)
@@ -156,7 +156,7 @@ def solve_case(inst, p, seeds, tail=0.0):
     bt.close(), pb.close(), op.close()
 
 
-@pytest.mark.parametrize("family", ["01", "101"])
+@pytest.mark.parametrize("family", ["01", "101", "Z"])
 def test_solve_whole(family):
     for equality in (False, True):
         inst = synth.small_mixed(m=14, n=40, seed=21, family=family, equality=equality, cost_hi=5)
@@ -173,6 +173,26 @@ def test_solve_scp_spp_shaped():
     solve_case(synth.spp(m=60, n=500, lo=3, hi=6, seed=2), p, [1, 2])
     p = util.params(limit=400, kappa_step=0.05, kappa_max=0.3, w=0)
     solve_case(synth.spp(m=60, n=500, lo=3, hi=6, seed=2), p, [1, 2])
+
+
+def test_sweeps_z_sub_solvers():
+    """Z rows of every kind: linear, exhaustive (< 10 elements), branch and
+    bound (10..16 elements), constrained and unconstrained, and a row long
+    enough for the CTA-wide ordering (> 32 elements)."""
+    inst = synth.telebus(m=90, n=400, seed=4)
+    for order in ("none", "infeasibility-decr", "infeasibility-incr"):
+        p = util.params(limit=100, kappa_step=0.002, w=2, order=order)
+        lockstep_engine(inst, p, [21, 22, 23], 40, pushes_every=6)
+    inst = synth.telebus(m=40, n=300, seed=6, linear_hi=90)
+    lockstep_engine(inst, util.params(kappa_step=0.01), [5, 6], 25, pushes_every=5)
+    inst = synth.small_mixed(m=12, n=60, seed=14, family="Z", density=0.2, cost_hi=2, maximize=True)
+    lockstep_engine(inst, util.params(kappa_step=0.01), [5, 6], 25, pushes_every=5)
+
+
+def test_solve_telebus_shaped():
+    inst = synth.telebus(m=150, n=700, seed=4)
+    p = util.params(limit=150, pushes_limit=3, pushing_iteration_limit=5, order="infeasibility-decr")
+    solve_case(inst, p, [1, 2, 3, 4])
 
 
 def test_set_state_roundtrip_and_carry_over():
