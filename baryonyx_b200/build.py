@@ -12,7 +12,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbaryonyx_b200.so")
+# bxg_kernels.cu is compiled once per solver family (-DBXG_FAM=0|1|2), the
+# translation units in parallel
+UNITS = [("bxg_api.cu", "bxg_api.o", []),
+         ("bxg_kernels.cu", "bxg_kernels_f0.o", ["-DBXG_FAM=0"]),
+         ("bxg_kernels.cu", "bxg_kernels_f1.o", ["-DBXG_FAM=1"]),
+         ("bxg_kernels.cu", "bxg_kernels_f2.o", ["-DBXG_FAM=2"])]
 SOURCES = ["bxg_api.cu", "bxg_kernels.cu"]
+OBJDIR = os.path.join(HERE, "build")
 HEADERS = ["bxg_device.cuh", "bxg_kernels.cuh", "bxg_zsolver.cuh", os.path.join("..", "..", "include", "bxg.h")]
 
 NVCC_FLAGS = [
@@ -22,7 +29,6 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-O2",
-    "-shared",
 ]
 
 
@@ -44,12 +50,29 @@ def stale() -> bool:
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
-    env = dict(os.environ)
+    os.makedirs(OBJDIR, exist_ok=True)
     # the image exports CXX=/opt/gcc/bin/g++ (static libstdc++); nvcc must use
     # the system host compiler
-    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd, env=env)
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    procs = []
+    for src, obj, defs in UNITS:
+        cmd = ([nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", os.path.join(CSRC, src), "-o", os.path.join(OBJDIR, obj)] + ccbin)
+        log = open(os.path.join(OBJDIR, obj + ".log"), "w")
+        procs.append((cmd, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT)))
+    failed = None
+    for cmd, log, p in procs:
+        rc = p.wait()
+        log.close()
+        if verbose or rc != 0:
+            with open(log.name) as f:
+                print(f.read())
+        if rc != 0 and failed is None:
+            failed = subprocess.CalledProcessError(rc, cmd)
+    if failed is not None:
+        raise failed
+    subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] +
+                          [os.path.join(OBJDIR, obj) for _, obj, _ in UNITS] + ccbin)
     return LIB
 
 

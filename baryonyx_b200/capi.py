@@ -69,7 +69,7 @@ EXPORTS = [
     "bxg_batch_create", "bxg_batch_destroy", "bxg_batch_info", "bxg_batch_set_tail_value",
     "bxg_batch_begin", "bxg_batch_get_state", "bxg_batch_set_state", "bxg_batch_sweep",
     "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
-    "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_last_ms", "bxg_batch_launches",
+    "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_launches",
     "bxg_batch_words32", "bxg_batch_begin_device",
 ]
 
@@ -127,6 +127,8 @@ def lib():
     L.bxg_batch_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_double)]
     L.bxg_batch_reset_counters.argtypes = [C.c_void_p]
+    L.bxg_batch_path_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64)]
     L.bxg_batch_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.bxg_batch_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.bxg_batch_words32.argtypes = [C.c_void_p]
@@ -274,6 +276,14 @@ class Batch:
         u, s, b = C.c_int64(), C.c_int64(), C.c_double()
         check(lib().bxg_batch_counters(self.h, C.byref(u), C.byref(s), C.byref(b)))
         return {"updates": u.value, "sweeps": s.value, "algorithmic_bytes": b.value}
+
+    def path_counters(self):
+        """Updates and cycles by selection path: exact, sorted, two smallest, sign boundary."""
+        u = (C.c_int64 * 4)()
+        c = (C.c_int64 * 4)()
+        ph = (C.c_int64 * 4)()
+        check(lib().bxg_batch_path_counters(self.h, u, c, ph))
+        return {"updates": list(u), "cycles": list(c), "phase_cycles": list(ph)}
 
     def reset_counters(self):
         check(lib().bxg_batch_reset_counters(self.h))

@@ -863,7 +863,7 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(cudaMemset(b->d_ctl.p, 0, sizeof(LaneCtl) * L));
     CUDA_TRY(cudaMemset(b->d_bestx.p, 0, b->d_bestx.bytes()));
 
-    b->cfg = plan_launch(pb->dev, pb->device);
+    b->cfg = plan_launch(pb->dev, pb->device, n_lanes);
     if (!b->cfg.r_in_smem)
         CUDA_TRY(b->d_scratch.alloc(L * lane_scratch_bytes(pb->dev, b->cfg)));
     const size_t zbytes = z_scratch_bytes(pb->max_zrow);
@@ -1349,9 +1349,43 @@ bxg_batch_reset_counters(bxg_batch* b)
         c.updates = 0;
         c.sweeps = 0;
         c.alg_bytes = 0;
+        for (int i = 0; i < 4; ++i) {
+            c.n_path[i] = 0;
+            c.cyc_path[i] = 0;
+            c.cyc_phase[i] = 0;
+        }
     }
     CUDA_TRY(cudaMemcpy(b->d_ctl.p, b->h_ctl.data(), sizeof(LaneCtl) * b->n_lanes,
                         cudaMemcpyHostToDevice));
+    return BXG_OK;
+}
+
+int
+bxg_batch_path_counters(bxg_batch* b, int64_t* updates, int64_t* cycles, int64_t* phase_cycles)
+{
+    if (!b)
+        return fail(BXG_E_INVALID, "null batch");
+    CUDA_TRY(cudaSetDevice(b->pb->device));
+    int rc = fetch_ctl(b);
+    if (rc != BXG_OK)
+        return rc;
+    for (int i = 0; i < 4; ++i) {
+        int64_t u = 0, c = 0;
+        for (const LaneCtl& l : b->h_ctl) {
+            u += static_cast<int64_t>(l.n_path[i]);
+            c += static_cast<int64_t>(l.cyc_path[i]);
+        }
+        if (updates)
+            updates[i] = u;
+        if (cycles)
+            cycles[i] = c;
+        if (phase_cycles) {
+            int64_t ph = 0;
+            for (const LaneCtl& l : b->h_ctl)
+                ph += static_cast<int64_t>(l.cyc_phase[i]);
+            phase_cycles[i] = ph;
+        }
+    }
     return BXG_OK;
 }
 

@@ -16,9 +16,20 @@
 //  * R is persistent per lane, like the reference's R member: the slot one
 //    past the current row keeps whatever a previous longer row left there
 //    (the reference reads it, itm-solver-inequalities-01.cpp:198-203).
+//
+// This file is compiled once per solver family (-DBXG_FAM=0|1|2: 01, 101, Z
+// coefficients): every family gets its own kernels, so the register budget of
+// the 01 sweep is not set by the branch-and-bound code of the Z rows, and the
+// three translation units build in parallel.
+#ifndef BXG_FAM
+#error "compile with -DBXG_FAM=0, 1 or 2 (see baryonyx_b200/build.py)"
+#endif
+
 #include "bxg_device.cuh"
 #include "bxg_kernels.cuh"
+#if BXG_FAM == 2
 #include "bxg_zsolver.cuh"
+#endif
 
 #include <climits>
 #include <math_constants.h>
@@ -28,6 +39,8 @@
 namespace bxg {
 
 namespace {
+
+constexpr int kFam = BXG_FAM;
 
 // The CTA's dynamic shared memory: [Lane][Shared][row scratch][R values][pi]
 // [activities][x].  Views built from this symbol keep their address space, so
@@ -59,6 +72,18 @@ struct Lane
 {
     const DevProblem* pb;
     const DevParams* pr;
+    // what a constraint update reads of pb / pr, copied here so the hot loop
+    // finds it with one shared-memory load
+    const RowHdr* row_hdr;
+    const int4* row_info;
+    const int* row_eptr;
+    const int2* gp;
+    const int* row_a;
+    const int* csc_rs;
+    const int* csc_a;
+    const double* cost;
+    double theta, delta;
+    int maximize, tail_rows;
     double* P;
     double* pi;
     uint32_t* x;
@@ -69,7 +94,7 @@ struct Lane
     int* sid;                 // [sort_cap]  position in the row, moved with sk
     double* Rv;               // [max_row+2] value left at each slot of the reference's R
     double* pown;             // [max_row+1] theta-decayed P of the row's own entries
-    double* stage;            // [2][stage_cap] P and pi terms of the entries being summed
+    double* stage;            // [stage_cap] {P term, pi term} of the entries being summed
     int stage_cap;
     int* oR;
     int2* mo;
@@ -86,6 +111,13 @@ struct Lane
     unsigned long long updates;
     unsigned long long sweeps;
     double alg_bytes;
+    // updates by selection path: 0 exact single thread, 1 CTA sort, 2 two
+    // smallest, 3 boundary by sign; and the cycles thread 0 spent in each
+    unsigned int n_path[4];
+    unsigned long long cyc_path[4];
+    // cycles of thread 0 by phase of the unordered paths: gather, sums,
+    // ties + candidates, affect (each up to its closing barrier)
+    unsigned long long cyc_phase[4];
 };
 
 constexpr size_t kLaneBytes = align16(sizeof(Lane));
@@ -289,7 +321,7 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
         seq_shuffle(a, ret, i - ret, rng);
     }
 
-    const int c_size = pb.family == FAM_101 ? pb.row_hdr[k].c_size : 0;
+    const int c_size = kFam == FAM_101 ? pb.row_hdr[k].c_size : 0;
     const int bkmin = pb.row_hdr[k].bmin, bkmax = pb.row_hdr[k].bmax;
     int selected;
     if (bkmin == bkmax) {
@@ -297,7 +329,7 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
         selected = (b < r_size ? b : r_size) - 1;
     } else {
         int lo, hi;
-        select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+        select_window(kFam, r_size, c_size, bkmin, bkmax, lo, hi);
         selected = hi - 1;
         for (int i = lo; i <= hi; ++i) {
             const double v = i < r_size ? value_at(i) : L.Rv[r_size];
@@ -487,7 +519,7 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
         } else if (total_draws)
             rng = lcg_mul(rng0, lcg_pow((uint64_t)total_draws));
 
-        const int c_size = pb.family == FAM_101 ? pb.row_hdr[k].c_size : 0;
+        const int c_size = kFam == FAM_101 ? pb.row_hdr[k].c_size : 0;
         const int bkmin = pb.row_hdr[k].bmin, bkmax = pb.row_hdr[k].bmax;
         int selected;
         if (bkmin == bkmax) {
@@ -495,7 +527,7 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
             selected = (b < r_size ? b : r_size) - 1;
         } else {
             int lo, hi;
-            select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+            select_window(kFam, r_size, c_size, bkmin, bkmax, lo, hi);
             selected = hi - 1;
             // the first n_pre sorted values neither stop the scan nor draw
             int i = lo;
@@ -532,11 +564,10 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
 // plus the row activities of the column when the bit flips.
 template<int FAM, bool SM>
 __device__ __forceinline__ void
-affect_element(Lane& L, int r0, int id, double pv, bool in, double d)
+affect_element(Lane& L, int r0, int id, const int4 info, double pv, bool in, double d)
 {
-    const DevProblem& pb = *L.pb;
-    const int4 info = pb.row_info[r0 + id]; // c0, c1, own CSC position, column
-    const bool neg = FAM != FAM_01 && pb.row_a[r0 + id] < 0;
+    // info = row_info[r0 + id]: c0, c1, own CSC position, column
+    const bool neg = FAM != FAM_01 && L.row_a[r0 + id] < 0;
     const bool set = in != neg;
     double* const gP = L.P;
     gP[info.z] = set ? __dadd_rn(pv, d) : __dsub_rn(pv, d);
@@ -550,13 +581,13 @@ affect_element(Lane& L, int r0, int id, double pv, bool in, double d)
         atomicXor(&x[j >> 5], bit);
         const int sgn = set ? 1 : -1;
         for (int t = info.x; t < info.y; ++t) {
-            const int rs = pb.csc_rs[t];
+            const int rs = L.csc_rs[t];
             if (FAM == FAM_01)
                 atomicAdd(&act[rs >> 1], sgn);
             else if (FAM == FAM_101)
                 atomicAdd(&act[rs >> 1], (rs & 1) ? -sgn : sgn);
             else
-                atomicAdd(&act[rs >> 1], sgn * pb.csc_a[t]);
+                atomicAdd(&act[rs >> 1], sgn * L.csc_a[t]);
         }
     }
 }
@@ -601,35 +632,43 @@ merge_min2(unsigned long long& m1, unsigned long long& m2, unsigned long long o1
 //    pi and P have moved): two smallest keys, or the boundary by sign.
 template<int FAM, bool SM>
 __device__ __noinline__ void
-update_row(int k, double kappa, int push, double obj_amp)
+update_row(int k, int k_next, double kappa, int push, double obj_amp)
 {
     Lane& L = the_lane();
-    const DevProblem& pb = *L.pb;
-    const DevParams& pr = *L.pr;
     const int tid = threadIdx.x, T = blockDim.x;
     const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
-    const RowHdr hdr = pb.row_hdr[k];
+    const RowHdr hdr = L.row_hdr[k];
     const int r0 = hdr.r0;
     const int r_size = hdr.r_size;
-    const double theta = pr.theta;
-    const bool maximize = pb.maximize != 0;
-    const double* __restrict__ cost = pr.cost;
+    const double theta = L.theta;
+    const bool maximize = L.maximize != 0;
+    const double* __restrict__ cost = L.cost;
+    const int4* __restrict__ row_info = L.row_info;
+    const int* __restrict__ row_eptr = L.row_eptr;
     // shared-memory views (the Lane block itself always lives there)
     const int stage_cap = L.stage_cap;
-    double* const sp = view<SM>(L.stage, L.o_stage);      // [stage_cap] P terms
-    int* const srs = reinterpret_cast<int*>(sp + stage_cap); // [stage_cap] row << 1 | negative
+    // [stage_cap] {P term, pi term} of the column entries being summed
+    double2* const st = reinterpret_cast<double2*>(view<SM>(L.stage, L.o_stage));
     double* const s_pi = view<SM>(L.pi, L.o_pi);
     unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
     double* const pown = view<SM>(L.pown, L.o_pown);
     double* const gP = L.P;
     Shared* const sh = the_shared();
-    const int2* __restrict__ gp = pb.gp + hdr.g0;
+    const int2* __restrict__ gp = L.gp + hdr.g0;
     const int S = hdr.S;
     const int bkmin = hdr.bmin, bkmax = hdr.bmax;
     const bool is_eq = bkmin == bkmax;
 
     if (tid == 0)
         L.alg_bytes += hdr.bytes;
+    const long long t_start = tid == 0 ? clock64() : 0;
+    long long t_gather = t_start, t_sums = 0, t_ties = 0;
+    // {r0, r_size} of the row the sweep visits next: its P lines are sent
+    // for while this row is being processed (see "prefetch" below)
+    int2 nh = make_int2(0, 0);
+    if (k_next >= 0)
+        nh = *reinterpret_cast<const int2*>(L.row_hdr + k_next);
+    int4 ni = make_int4(0, 0, 0, 0);
 
     int odd = 0;    // NaN or -0.0 seen by this thread
     int counts = 0; // low half: values that neither stop the scan nor are zero; high half: zeros
@@ -642,70 +681,76 @@ update_row(int k, double kappa, int push, double obj_amp)
     for (int ia = 0; ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
         int ib = r_size;
-        const int fa = pb.row_eptr[r0 + ia];
+        const int fa = row_eptr[r0 + ia];
         int fb = S;
         if (S - fa > stage_cap) {
             int lo = ia + 1, hi = r_size; // last ib with eptr[ib] - fa <= cap
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (pb.row_eptr[r0 + mid] - fa <= stage_cap)
+                if (row_eptr[r0 + mid] - fa <= stage_cap)
                     lo = mid;
                 else
                     hi = mid - 1;
             }
             ib = lo;
-            fb = pb.row_eptr[r0 + ib];
+            fb = row_eptr[r0 + ib];
         }
 
 // @region update_row.stage1
-        // stage 1: entries
+        // stage 1: entries.  The index is clamped rather than predicated, so
+        // the loads of a trip are unconditional and independent.
+        const int g_last = fb - 1;
         for (int g = fa + tid; g < fb; g += 4 * T) {
             int2 e[4];
             double p[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int gg = g + u * T;
-                e[u] = gg < fb ? gp[gg] : make_int2(0, 0);
+                e[u] = gp[gg < g_last ? gg : g_last];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                p[u] = (g + u * T) < fb ? gP[e[u].x] : 0.0;
+                p[u] = gP[e[u].x];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int gg = g + u * T;
-                if (gg < fb) {
-                    const int row = e[u].y >> 1;
-                    double pv = p[u];
-                    if (row == k)
-                        pv = __dmul_rn(pv, theta);
-                    if (FAM != FAM_01 && (e[u].y & 1))
-                        pv = -pv;
-                    sp[gg - fa] = pv;
-                    srs[gg - fa] = e[u].y;
+                const int rs = e[u].y;
+                double a_pi = s_pi[rs >> 1];
+                double pv = p[u];
+                if ((rs >> 1) == k)
+                    pv = __dmul_rn(pv, theta);
+                if (FAM != FAM_01 && (rs & 1)) {
+                    pv = -pv;
+                    a_pi = -a_pi;
                 }
+                if (gg < fb)
+                    st[gg - fa] = make_double2(pv, a_pi);
             }
         }
+// @region update_row.prefetch
+        // prefetch, first half: where the next row's columns lie in P
+        if (ia == 0 && tid < nh.y)
+            ni = row_info[nh.x + tid];
         __syncthreads();
+        if (ia == 0 && tid == 0)
+            t_gather = clock64();
 
 // @region update_row.stage2
-        // stage 2: elements
-        for (int i = ia + tid; i < ib; i += T) {
-            const int4 info = pb.row_info[r0 + i]; // c0, c1, own CSC position, column
-            const int s0 = pb.row_eptr[r0 + i] - fa;
+        // stage 2: elements.  A thread owns elements i and i + T of the chunk
+        // and fetches what both need before summing either, so a row a little
+        // longer than the CTA does not pay the load latency twice.
+        auto element = [&](int i, const int4 info, int eptr, double cj) {
+            const double2* const c = st + (eptr - fa);
             const int len = info.y - info.x;
-            const double cj = cost[info.w];
             double sum_pi = 0.0, sum_p = 0.0;
             for (int t = 0; t < len; ++t) {
-                const int rs = srs[s0 + t];
-                double a_pi = s_pi[rs >> 1];
-                if (FAM != FAM_01 && (rs & 1))
-                    a_pi = -a_pi;
-                sum_pi = __dadd_rn(sum_pi, a_pi);
-                sum_p = __dadd_rn(sum_p, sp[s0 + t]);
+                const double2 term = c[t];
+                sum_pi = __dadd_rn(sum_pi, term.y);
+                sum_p = __dadd_rn(sum_p, term.x);
             }
-            double own = sp[s0 + (info.z - info.x)];
+            double own = c[info.z - info.x].x;
             double v = __dsub_rn(__dsub_rn(cj, sum_pi), sum_p);
-            if (FAM != FAM_01 && pb.row_a[r0 + i] < 0) {
+            if (FAM != FAM_01 && L.row_a[r0 + i] < 0) {
                 v = -v;
                 own = -own;
             }
@@ -729,10 +774,37 @@ update_row(int k, double kappa, int push, double obj_amp)
             }
             key0[i] = (unsigned long long)__double_as_longlong(v);
             pown[i] = own;
+        };
+        for (int i = ia + tid; i < ib; i += 2 * T) {
+            const int i2 = i + T < ib ? i + T : i;
+            const int4 info1 = row_info[r0 + i];
+            const int4 info2 = row_info[r0 + i2];
+            const int eptr1 = row_eptr[r0 + i];
+            const int eptr2 = row_eptr[r0 + i2];
+            const double cj1 = cost[info1.w];
+            const double cj2 = cost[info2.w];
+            element(i, info1, eptr1, cj1);
+            if (i2 != i)
+                element(i2, info2, eptr2, cj2);
         }
         ia = ib;
         if (ia < r_size)
             __syncthreads(); // the staging buffer is reused
+    }
+
+// @region update_row.prefetch2
+    // prefetch, second half: every 32-byte sector of the next row's columns
+    // goes to L2 now; its gather starts after this row's selection and affect.
+    if (k_next >= 0) {
+        for (int i = tid; i < nh.y; i += T) {
+            if (i >= T)
+                ni = row_info[nh.x + i];
+            const char* a = reinterpret_cast<const char*>(gP + ni.x);
+            const char* const end = reinterpret_cast<const char*>(gP + ni.y);
+            a = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(31));
+            for (; a < end; a += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
     }
 
 // @region update_row.reduceA
@@ -745,6 +817,8 @@ update_row(int k, double kappa, int push, double obj_amp)
     const int tab_gen0 = L.tab_gen;
     const int tab_dirty0 = L.tab_dirty;
     const bool raw = __syncthreads_or(odd) != 0;
+    if (tid == 0)
+        t_sums = clock64();
     int n_pre = 0, n_zero = 0;
     if (!is_eq) {
         counts = 0;
@@ -765,7 +839,7 @@ update_row(int k, double kappa, int push, double obj_amp)
         mode = 0;
     } else {
         mode = 1;
-        if (pb.tail_rows == 0) {
+        if (L.tail_rows == 0) {
             const int c_size = FAM == FAM_101 ? hdr.c_size : 0;
             if (is_eq) {
                 const int b = bkmin + c_size;
@@ -774,7 +848,7 @@ update_row(int k, double kappa, int push, double obj_amp)
                     mode = 2;
             } else if (n_zero == 0) {
                 int lo, hi;
-                select_window(pb.family, r_size, c_size, bkmin, bkmax, lo, hi);
+                select_window(kFam, r_size, c_size, bkmin, bkmax, lo, hi);
                 const int i0 = lo > n_pre ? lo : n_pre; // first index holding a stopping value
                 selected = (i0 <= hi ? i0 : hi) - 1;
                 if (selected + 1 == n_pre)
@@ -847,8 +921,10 @@ update_row(int k, double kappa, int push, double obj_amp)
             sh->redk[wp][1] = b;
         }
         const bool any_dup = __syncthreads_or(dup) != 0;
-        if (tid == 0)
+        if (tid == 0) {
             L.tab_gen = tab_gen;
+            t_ties = clock64();
+        }
         if (any_dup)
             mode = 1; // equal values: their runs draw from the engine
         else {
@@ -881,19 +957,37 @@ update_row(int k, double kappa, int push, double obj_amp)
             double npi;
             bool moves;
             const double d =
-              affect_step(pr.delta, sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
+              affect_step(L.delta, sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
             if (tid == 0 && moves) {
                 s_pi[k] = npi; // all threads read pi[k] before the barrier above
                 if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
                     sh->pi_changed = 1;
             }
 // @region update_row.fastD
-            for (int i = tid; i < r_size; i += T) {
-                const unsigned long long key =
+            for (int i = tid; i < r_size; i += 2 * T) {
+                const int i2 = i + T < r_size ? i + T : i;
+                const int4 info1 = row_info[r0 + i];
+                const int4 info2 = row_info[r0 + i2];
+                const unsigned long long key1 =
                   key_of(__longlong_as_double((long long)key0[i]), maximize);
-                affect_element<FAM, SM>(L, r0, i, pown[i], selected >= 0 && key <= key_sel, d);
+                affect_element<FAM, SM>(L, r0, i, info1, pown[i], selected >= 0 && key1 <= key_sel, d);
+                if (i2 != i) {
+                    const unsigned long long key2 =
+                      key_of(__longlong_as_double((long long)key0[i2]), maximize);
+                    affect_element<FAM, SM>(L, r0, i2, info2, pown[i2],
+                                            selected >= 0 && key2 <= key_sel, d);
+                }
             }
             __syncthreads();
+            if (tid == 0) {
+                const long long t_end = clock64();
+                L.n_path[mode] += 1;
+                L.cyc_path[mode] += (unsigned long long)(t_end - t_start);
+                L.cyc_phase[0] += (unsigned long long)(t_gather - t_start);
+                L.cyc_phase[1] += (unsigned long long)(t_sums - t_gather);
+                L.cyc_phase[2] += (unsigned long long)(t_ties - t_sums);
+                L.cyc_phase[3] += (unsigned long long)(t_end - t_ties);
+            }
             return;
         }
     }
@@ -929,17 +1023,22 @@ update_row(int k, double kappa, int push, double obj_amp)
     {
         const int sel = L.sh->selected;
         const double d = L.sh->d;
-        const bool keep_tail = pb.tail_rows != 0;
+        const bool keep_tail = L.tail_rows != 0;
         for (int p = tid; p < r_size; p += T) {
             const int id = L.sid[p];
-            affect_element<FAM, SM>(L, r0, id, pown[id], p <= sel, d);
+            affect_element<FAM, SM>(L, r0, id, L.row_info[r0 + id], pown[id], p <= sel, d);
             if (keep_tail)
                 L.Rv[p] = raw ? __longlong_as_double((long long)L.sk[p]) : value_of_key(L.sk[p], maximize);
         }
     }
     __syncthreads();
+    if (tid == 0) {
+        L.n_path[slow ? 0 : 1] += 1;
+        L.cyc_path[slow ? 0 : 1] += (unsigned long long)(clock64() - t_start);
+    }
 }
 
+#if BXG_FAM == 2
 // @region update_row_z
 // select_variables / select_variables_101 of the Z solver (identical bodies,
 // itm-solver-inequalities-Z.cpp:308-344): the longest prefix of the ordered
@@ -1169,6 +1268,8 @@ update_row_z(int k, double kappa, int push, double obj_amp)
 }
 
 
+#endif // BXG_FAM == 2
+
 // @region activities
 // Row activities from scratch (is_valid_constraint's sum, itm-common.hpp:76-89);
 // afterwards the updates keep them current.
@@ -1182,7 +1283,7 @@ activities_recompute(Lane& L)
     for (int k = warp; k < pb.m; k += nwarps) {
         const int e0 = pb.row_ptr[k], e1 = pb.row_ptr[k + 1];
         int v = 0;
-        if (pb.family == FAM_01) {
+        if (kFam == FAM_01) {
             for (int e = e0 + lane; e < e1; e += 32)
                 v += xbit(L.x, pb.row_col[e]);
         } else {
@@ -1197,7 +1298,7 @@ activities_recompute(Lane& L)
     }
     __syncthreads();
     if (tid == 0)
-        L.alg_bytes += 4.0 * pb.nnz * (pb.family == FAM_01 ? 1.0 : 2.0) + pb.n / 8.0;
+        L.alg_bytes += 4.0 * pb.nnz * (kFam == FAM_01 ? 1.0 : 2.0) + pb.n / 8.0;
 }
 
 // @region violated_scan
@@ -1342,21 +1443,21 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
             k = L.mo[i].x;
         else
             k = L.oR[order == ORDER_REVERSING ? len - 1 - i : i];
-        if (L.all_smem) {
-            if (L.pb->family == FAM_01)
-                update_row<FAM_01, true>(k, kappa, push, obj_amp);
-            else if (L.pb->family == FAM_101)
-                update_row<FAM_101, true>(k, kappa, push, obj_amp);
-            else
-                update_row_z<true>(k, kappa, push, obj_amp);
-        } else {
-            if (L.pb->family == FAM_01)
-                update_row<FAM_01, false>(k, kappa, push, obj_amp);
-            else if (L.pb->family == FAM_101)
-                update_row<FAM_101, false>(k, kappa, push, obj_amp);
-            else
-                update_row_z<false>(k, kappa, push, obj_amp);
-        }
+        const int k_next = i + 1 < len ? (pairs ? L.mo[i + 1].x
+                                                : L.oR[order == ORDER_REVERSING ? len - 2 - i : i + 1])
+                                       : -1;
+#if BXG_FAM == 2
+        (void)k_next;
+        if (L.all_smem)
+            update_row_z<true>(k, kappa, push, obj_amp);
+        else
+            update_row_z<false>(k, kappa, push, obj_amp);
+#else
+        if (L.all_smem)
+            update_row<kFam, true>(k, k_next, kappa, push, obj_amp);
+        else
+            update_row<kFam, false>(k, k_next, kappa, push, obj_amp);
+#endif
     }
 
     if (pairs) {
@@ -1431,7 +1532,7 @@ __host__ __device__ inline size_t
 row_scratch_bytes(int max_row, int sort_cap, int stage_cap)
 {
     size_t n = 0;
-    n += (sizeof(double) + sizeof(int)) * (size_t)stage_cap; // stage: P terms, rows
+    n += sizeof(double2) * (size_t)stage_cap; // stage: {P term, pi term}
     n = (n + 15) & ~size_t(15);
     n += sizeof(unsigned long long) * (size_t)max_row;  // key0
     n += sizeof(unsigned long long) * (size_t)sort_cap; // sk
@@ -1500,6 +1601,18 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
     if (tid == 0) {
         L.pb = &pb;
         L.pr = &pr;
+        L.row_hdr = pb.row_hdr;
+        L.row_info = pb.row_info;
+        L.row_eptr = pb.row_eptr;
+        L.gp = pb.gp;
+        L.row_a = pb.row_a;
+        L.csc_rs = pb.csc_rs;
+        L.csc_a = pb.csc_a;
+        L.cost = pr.cost;
+        L.theta = pr.theta;
+        L.delta = pr.delta;
+        L.maximize = pb.maximize;
+        L.tail_rows = pb.tail_rows;
         L.sh = sh;
         L.P = b.P + (size_t)lane_id * pb.nnz;
         L.ctl = ctl;
@@ -1518,7 +1631,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         size_t o = 0;
         L.stage = reinterpret_cast<double*>(scratch + o);
         L.stage_cap = plan.stage_cap;
-        o += (sizeof(double) + sizeof(int)) * (size_t)plan.stage_cap;
+        o += sizeof(double2) * (size_t)plan.stage_cap;
         o = (o + 15) & ~size_t(15);
         L.key0 = reinterpret_cast<unsigned long long*>(scratch + o);
         o += sizeof(unsigned long long) * (size_t)pb.max_row;
@@ -1548,6 +1661,11 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.updates = 0;
         L.sweeps = 0;
         L.alg_bytes = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            L.n_path[i] = 0;
+            L.cyc_path[i] = 0;
+            L.cyc_phase[i] = 0;
+        }
     }
     ls.oR_len = ctl->oR_len;
     ls.mo_len = ctl->mo_len;
@@ -1591,6 +1709,11 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
         L.ctl->updates += L.updates;
         L.ctl->sweeps += L.sweeps;
         L.ctl->alg_bytes += L.alg_bytes;
+        for (int i = 0; i < 4; ++i) {
+            L.ctl->n_path[i] += L.n_path[i];
+            L.ctl->cyc_path[i] += L.cyc_path[i];
+            L.ctl->cyc_phase[i] += L.cyc_phase[i];
+        }
     }
 }
 
@@ -1869,6 +1992,7 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
 // ---------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------
+#if BXG_FAM == 2
 static int
 pow2_at_least(int v)
 {
@@ -1910,8 +2034,16 @@ lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg)
     return row_scratch_bytes(pb.max_row, cfg.sort_cap, cfg.stage_cap);
 }
 
+// CTAs per SM the register budget of a CTA size class allows (the MINB of
+// its __launch_bounds__, see BXG_LAUNCH_HOT).
+static int
+cta_class_blocks(int threads)
+{
+    return threads <= 96 ? 8 : threads <= 128 ? 7 : threads <= 192 ? 5 : threads <= 256 ? 3 : 1;
+}
+
 LaunchCfg
-plan_launch(const DevProblem& pb, int device)
+plan_launch(const DevProblem& pb, int device, int n_lanes)
 {
     int max_optin = 0, per_sm = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -1937,13 +2069,14 @@ plan_launch(const DevProblem& pb, int device)
     };
     {
         // a smaller staging buffer (rows summed in chunks) when that lets
-        // eight lanes share an SM
-        const size_t target = (size_t)per_sm / 8 - 1024;
+        // seven lanes share an SM (what the registers of the 128- and
+        // 160-thread classes allow)
+        const size_t target = (size_t)per_sm / 7 - 1024;
         if (bytes() > target) {
             cfg.stage_cap = stage_min;
             const size_t fixed = bytes();
             if (fixed < target) {
-                cfg.stage_cap += (int)((target - fixed) / 12);
+                cfg.stage_cap += (int)((target - fixed) / sizeof(double2));
                 if (cfg.stage_cap > pb.max_S)
                     cfg.stage_cap = pb.max_S;
             }
@@ -1962,18 +2095,41 @@ plan_launch(const DevProblem& pb, int device)
         cfg.pi_in_smem = 0;
     cfg.smem = bytes();
 
-    // enough threads for the row elements of the second gather stage, whole
-    // warps; BXG_THREADS overrides (experiments)
-    int t = ((pb.p95_row / 2 + 31) / 32) * 32;
-    if (const char* env = getenv("BXG_THREADS"))
-        t = (atoi(env) + 31) / 32 * 32;
+    // One thread per row element in the second gather stage (whole warps),
+    // narrowed while that lets every lane of the batch be resident at once:
+    // a second wave of CTAs costs more than a second trip over a long row.
+    // BXG_THREADS overrides (experiments).
+    int t = ((pb.p95_row + 31) / 32) * 32;
     if (t < 64)
         t = 64;
+    if (t > 1024)
+        t = 1024;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (sms <= 0)
+        sms = 148;
+    auto resident = [&](int threads) {
+        const int by_regs = cta_class_blocks(threads);
+        const int by_smem = (int)((size_t)per_sm / (cfg.smem + 1024));
+        return (long)sms * (by_regs < by_smem ? by_regs : (by_smem < 1 ? 1 : by_smem));
+    };
+    while (t > 128 && n_lanes > resident(t) && resident(t - 32) > resident(t))
+        t -= 32;
+    if (const char* env = getenv("BXG_THREADS"))
+        t = (atoi(env) + 31) / 32 * 32;
+    if (t < 32)
+        t = 32;
     if (t > 1024)
         t = 1024;
     cfg.threads = t;
     return cfg;
 }
+
+#endif // BXG_FAM == 2 (the shared host helpers live in one translation unit)
+
+#define BXG_CAT2(a, b) a##_f##b
+#define BXG_CAT(a, b) BXG_CAT2(a, b)
+#define BXG_FAM_FN(name) BXG_CAT(name, BXG_FAM)
 
 template<typename K>
 static void
@@ -1984,21 +2140,24 @@ set_smem(K kernel, size_t smem)
                          cudaSharedmemCarveoutMaxShared);
 }
 
-// CTA size classes: each kernel is compiled once per class so that the
-// register budget follows the CTA size (small CTAs, several per SM, get more
-// registers per thread; 1024-thread CTAs are held to 64).
+// CTA size classes: the sweep kernels are compiled once per class so that the
+// register budget follows the CTA size (MINB CTAs of MAXT threads share the
+// 64 K registers of an SM); the kernels outside the sweep loop are compiled
+// once, for the largest CTA.
 #define BXG_LAUNCH_CLASS(KERNEL, MAXT, MINB, GRID, CFG, STREAM, ...)                         \
     do {                                                                                    \
         set_smem(KERNEL<MAXT, MINB>, (CFG).smem);                                           \
         KERNEL<MAXT, MINB><<<(GRID), (CFG).threads, (CFG).smem, (STREAM)>>>(__VA_ARGS__);   \
     } while (0)
 
-#define BXG_LAUNCH(KERNEL, GRID, CFG, STREAM, ...)                                          \
+#define BXG_LAUNCH_HOT(KERNEL, GRID, CFG, STREAM, ...)                                      \
     do {                                                                                    \
         if ((CFG).threads <= 96)                                                            \
             BXG_LAUNCH_CLASS(KERNEL, 96, 8, GRID, CFG, STREAM, __VA_ARGS__);                \
         else if ((CFG).threads <= 128)                                                      \
-            BXG_LAUNCH_CLASS(KERNEL, 128, 6, GRID, CFG, STREAM, __VA_ARGS__);               \
+            BXG_LAUNCH_CLASS(KERNEL, 128, 7, GRID, CFG, STREAM, __VA_ARGS__);               \
+        else if ((CFG).threads <= 192)                                                      \
+            BXG_LAUNCH_CLASS(KERNEL, 192, 5, GRID, CFG, STREAM, __VA_ARGS__);               \
         else if ((CFG).threads <= 256)                                                      \
             BXG_LAUNCH_CLASS(KERNEL, 256, 3, GRID, CFG, STREAM, __VA_ARGS__);               \
         else if ((CFG).threads <= 512)                                                      \
@@ -2007,47 +2166,50 @@ set_smem(K kernel, size_t smem)
             BXG_LAUNCH_CLASS(KERNEL, 1024, 1, GRID, CFG, STREAM, __VA_ARGS__);              \
     } while (0)
 
+#define BXG_LAUNCH_COLD(KERNEL, GRID, CFG, STREAM, ...)                                     \
+    BXG_LAUNCH_CLASS(KERNEL, 1024, 1, GRID, CFG, STREAM, __VA_ARGS__)
+
 void
-launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+BXG_FAM_FN(launch_begin)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const uint32_t* d_seeds, const uint32_t* d_x0, const uint32_t* d_rng,
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
+    BXG_LAUNCH_COLD(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
                init_on_device, init_random, d_cost_orig, plan);
 }
 
 void
-launch_order_init(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+BXG_FAM_FN(launch_order_init)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
+    BXG_LAUNCH_COLD(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
 }
 
 void
-launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
+BXG_FAM_FN(launch_sweep)(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
+    BXG_LAUNCH_HOT(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
 }
 
 void
-launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan);
+    BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
 void
-launch_objective(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+BXG_FAM_FN(launch_objective)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
+    BXG_LAUNCH_COLD(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
 } // namespace bxg

@@ -127,6 +127,9 @@ struct LaneCtl
     unsigned long long updates;
     unsigned long long sweeps;
     double alg_bytes;
+    unsigned long long n_path[4];   // updates by selection path (see Lane)
+    unsigned long long cyc_path[4]; // cycles of thread 0 inside them
+    unsigned long long cyc_phase[4]; // ... by phase: gather, sums, ties, affect
 };
 
 // Per-batch lane storage (struct of arrays over lanes).
@@ -160,25 +163,80 @@ struct LaunchCfg
     int stage_cap;
 };
 
-LaunchCfg plan_launch(const DevProblem& pb, int device);
+LaunchCfg plan_launch(const DevProblem& pb, int device, int n_lanes);
 size_t lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg);
 size_t z_scratch_bytes(int max_zrow);
 
-void launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
-                  const uint32_t* d_seeds, const uint32_t* d_x0,
-                  const uint32_t* d_rng, int reset_solver, int init_on_device,
-                  double init_random, const double* d_cost_orig,
-                  const LaunchCfg& cfg, cudaStream_t s);
-void launch_order_init(const DevProblem& pb, const DevParams& pr,
-                       const DevBatch& b, int lane_first, int lane_count,
-                       const LaunchCfg& cfg, cudaStream_t s);
-void launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
-                  int push, double obj_amp, const LaunchCfg& cfg,
-                  cudaStream_t s);
-void launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
-                  const LaunchCfg& cfg, cudaStream_t s);
-void launch_objective(const DevProblem& pb, const DevParams& pr,
-                      const DevBatch& b, const LaunchCfg& cfg, cudaStream_t s);
+// The kernels are compiled once per solver family (bxg_kernels.cu with
+// -DBXG_FAM=0|1|2); name_f0 / _f1 / _f2 are the entry points of the three
+// translation units, the inline functions below pick by DevProblem::family.
+#define BXG_DECLARE_FAMILY(F)                                                                    \
+    void launch_begin_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
+                           const uint32_t* d_seeds, const uint32_t* d_x0, const uint32_t* d_rng, \
+                           int reset_solver, int init_on_device, double init_random,             \
+                           const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s);     \
+    void launch_order_init_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,    \
+                                int lane_first, int lane_count, const LaunchCfg& cfg,            \
+                                cudaStream_t s);                                                 \
+    void launch_sweep_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
+                           int push, double obj_amp, const LaunchCfg& cfg, cudaStream_t s);      \
+    void launch_solve_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
+                           const LaunchCfg& cfg, cudaStream_t s);                                \
+    void launch_objective_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,     \
+                               const LaunchCfg& cfg, cudaStream_t s);
+BXG_DECLARE_FAMILY(0)
+BXG_DECLARE_FAMILY(1)
+BXG_DECLARE_FAMILY(2)
+#undef BXG_DECLARE_FAMILY
+
+#define BXG_BY_FAMILY(pb, name, ...)                                                             \
+    do {                                                                                         \
+        if ((pb).family == FAM_01)                                                               \
+            name##_f0(__VA_ARGS__);                                                              \
+        else if ((pb).family == FAM_101)                                                         \
+            name##_f1(__VA_ARGS__);                                                              \
+        else                                                                                     \
+            name##_f2(__VA_ARGS__);                                                              \
+    } while (0)
+
+inline void
+launch_begin(const DevProblem& pb, const DevParams& pr, const DevBatch& b, const uint32_t* d_seeds,
+             const uint32_t* d_x0, const uint32_t* d_rng, int reset_solver, int init_on_device,
+             double init_random, const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_begin, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver, init_on_device,
+                  init_random, d_cost_orig, cfg, s);
+}
+
+inline void
+launch_order_init(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int lane_first,
+                  int lane_count, const LaunchCfg& cfg, cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_order_init, pb, pr, b, lane_first, lane_count, cfg, s);
+}
+
+inline void
+launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push, double obj_amp,
+             const LaunchCfg& cfg, cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_sweep, pb, pr, b, push, obj_amp, cfg, s);
+}
+
+inline void
+launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b, const LaunchCfg& cfg,
+             cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_solve, pb, pr, b, cfg, s);
+}
+
+inline void
+launch_objective(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+                 const LaunchCfg& cfg, cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_objective, pb, pr, b, cfg, s);
+}
+
+#undef BXG_BY_FAMILY
 
 } // namespace bxg
 

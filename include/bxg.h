@@ -201,6 +201,15 @@ int bxg_batch_argbest(bxg_batch* b, int* lane, double* value, int* remaining);
 int bxg_batch_counters(bxg_batch* b, int64_t* updates, int64_t* sweeps,
                        double* algorithmic_bytes);
 int bxg_batch_reset_counters(bxg_batch* b);
+/* Updates by selection path of calculator_sort / select_variables
+ * (itm-common.hpp:134-148): [0] exact single-thread ordering, [1] CTA-wide
+ * sort, [2] two smallest values, [3] boundary at the sign change; and the SM
+ * cycles spent inside them (one thread's clock); phase_cycles splits the
+ * cycles of paths [2] and [3] into reduced-cost gather, column sums, tie
+ * detection + boundary values, and affect.  Each output holds 4 values, any
+ * may be NULL. */
+int bxg_batch_path_counters(bxg_batch* b, int64_t* updates, int64_t* cycles,
+                            int64_t* phase_cycles);
 /* Device time of the last bxg_batch_sweep / bxg_batch_solve, CUDA events on
  * the batch's stream, milliseconds. */
 int bxg_batch_last_ms(bxg_batch* b, float* ms);

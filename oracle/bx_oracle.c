@@ -2526,3 +2526,461 @@ ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
     ox_run_end(r);
     return status;
 }
+
+/* ======================================================================== */
+/* Optimizer population: local_context, storage,          */
+/* best_solution_recorder -- itm-optimizer-common.hpp:52-594                */
+/* ======================================================================== */
+
+typedef struct ox_member
+{
+    uint64_t* x;
+    double value;
+    uint64_t hash;
+    int64_t loop;
+    int remaining;
+} ox_member;
+
+struct ox_pop
+{
+    ox_problem* pb;
+    ox_params p;
+    int size;
+    int blocks;
+    int threads;
+    int* indices;
+    ox_member* data;
+    uint64_t* bastert;
+    uint64_t* random;
+    double* kappa_append;
+};
+
+/* local_context, itm-optimizer-common.hpp:52-92 */
+struct ox_pop_ctx
+{
+    uint32_t rng;
+    ox_normal_dist choose_sol;
+    ox_normal_dist variable_p;
+    ox_normal_dist value_p;
+    int bad_lo, bad_hi;
+    double bastert_insertion;
+    double improve_start, improve_increase, improve_stop;
+    unsigned thread_id;
+};
+
+static uint32_t
+engine_seed(uint64_t seed)
+{
+    /* linear_congruential_engine::seed: value mod m, 0 is mapped to 1 */
+    uint32_t s = (uint32_t)(seed % OX_RNG_M);
+    return s == 0 ? 1u : s;
+}
+
+static int
+wget(const uint64_t* x, int i)
+{
+    return (int)((x[i / 64] >> (i % 64)) & 1u);
+}
+
+/* bit_array_hash, bit-array.hpp:410-423 (std::hash<size_t> is the identity) */
+uint64_t
+ox_bit_array_hash(int n, const uint64_t* x)
+{
+    uint64_t ret = 0;
+    for (int i = 0, e = n / 64 + 1; i != e; ++i)
+        ret ^= x[i] + 0x9e3779b9u + (ret << 6) + (ret >> 2);
+    return ret;
+}
+
+/* default_cost_type::results, itm-common.hpp:1140-1147 */
+static double
+pop_results(const ox_problem* pb, const uint64_t* x)
+{
+    double v = pb->cost_constant;
+    for (int i = 0; i != pb->n_obj; ++i)
+        if (wget(x, pb->obj_var[i]))
+            v += pb->obj_factor[i];
+    return v;
+}
+
+static int
+pop_remaining(const ox_problem* pb, const uint64_t* x)
+{
+    int remaining = 0;
+    for (int k = 0; k != pb->m; ++k) {
+        int sum = 0;
+        for (int e = pb->row_ptr[k]; e != pb->row_ptr[k + 1]; ++e)
+            if (wget(x, pb->row_col[e]))
+                sum += pb->A[e];
+        if (!(pb->cmin[k] <= sum && sum <= pb->cmax[k]))
+            ++remaining;
+    }
+    return remaining;
+}
+
+static int
+is_better_solution(int maximize, double lhs, double rhs)
+{
+    return maximize ? lhs > rhs : lhs < rhs;
+}
+
+/* storage::sort's comparator, itm-optimizer-common.hpp:425-441 */
+static int
+pop_index_less(const void* a, const void* b, void* ctx)
+{
+    const struct ox_pop* pop = (const struct ox_pop*)ctx;
+    const ox_member* m1 = &pop->data[*(const int*)a];
+    const ox_member* m2 = &pop->data[*(const int*)b];
+
+    if (m1->remaining < m2->remaining)
+        return 1;
+    if (m1->remaining == m2->remaining)
+        return is_better_solution(pop->pb->maximize, m1->value, m2->value);
+    return 0;
+}
+
+static void
+pop_sort(struct ox_pop* pop)
+{
+    ox_std_sort(pop->indices, pop->size, sizeof(int), pop_index_less, pop);
+}
+
+/* init_with_random, itm-common.hpp:269-282 */
+static void
+pop_init_with_random(uint64_t* x, uint32_t* rng, int n, double p)
+{
+    for (int i = 0; i != n; ++i) {
+        if (ox_bernoulli(p, rng))
+            x[i / 64] |= (uint64_t)1 << (i % 64);
+        else
+            x[i / 64] &= ~((uint64_t)1 << (i % 64));
+    }
+}
+
+/* init_with_pre_solve with both vectors present, itm-common.hpp:284-374 */
+static void
+pop_pre_solve(const ox_problem* pb, uint64_t* xp, uint64_t* xo, uint32_t* rng,
+              double init_random)
+{
+    ox_pre_rc* R =
+      (ox_pre_rc*)malloc(sizeof(ox_pre_rc) * (size_t)(pb->max_row + 1));
+
+    for (int k = 0; k != pb->m; ++k) {
+        if (!ox_bernoulli(init_random, rng))
+            continue;
+
+        const int r_size = pb->row_ptr[k + 1] - pb->row_ptr[k];
+        for (int i = 0; i != r_size; ++i) {
+            const int e = pb->row_ptr[k] + i;
+            R[i].value = (float)pb->cost[pb->row_col[e]];
+            R[i].factor = pb->A[e];
+            R[i].id = pb->row_col[e];
+        }
+
+        ox_std_shuffle(R, r_size, sizeof(ox_pre_rc), rng);
+        ox_std_sort(R, r_size, sizeof(ox_pre_rc),
+                    pb->maximize ? pre_less_max : pre_less_min, NULL);
+
+        {
+            int sum = 0, best = -2;
+            for (int i = -1; i < r_size; ++i) {
+                if (pb->cmin[k] <= sum && sum <= pb->cmax[k]) {
+                    best = i;
+                    break;
+                }
+                if (i + 1 < r_size)
+                    sum += R[i + 1].factor;
+            }
+            int i = 0;
+            for (; i <= best; ++i)
+                xp[R[i].id / 64] |= (uint64_t)1 << (R[i].id % 64);
+            for (; i != r_size; ++i)
+                xp[R[i].id / 64] &= ~((uint64_t)1 << (R[i].id % 64));
+        }
+        {
+            int sum = 0, best = -2;
+            for (int i = -1; i < r_size; ++i) {
+                if (pb->cmin[k] <= sum && sum <= pb->cmax[k])
+                    best = i;
+                if (best != -2 && i + 1 < r_size &&
+                    (pb->maximize ? R[i + 1].value < 0 : R[i + 1].value > 0))
+                    break;
+                if (i + 1 < r_size)
+                    sum += R[i + 1].factor;
+            }
+            int i = 0;
+            for (; i <= best; ++i)
+                xo[R[i].id / 64] |= (uint64_t)1 << (R[i].id % 64);
+            for (; i != r_size; ++i)
+                xo[R[i].id / 64] &= ~((uint64_t)1 << (R[i].id % 64));
+        }
+    }
+    free(R);
+}
+
+/* best_solution_recorder / storage constructors,
+ * itm-optimizer-common.hpp:162-226,467-480, on random_engine(master_seed). */
+ox_pop*
+ox_pop_create(ox_problem* pb, const ox_params* p, uint64_t master_seed,
+              int threads, uint32_t* rng_state)
+{
+    struct ox_pop* pop = (struct ox_pop*)calloc(1, sizeof(struct ox_pop));
+    uint32_t rng = engine_seed(master_seed);
+    const int n = pb->n;
+
+    pop->pb = pb;
+    pop->p = *p;
+    pop->size = p->init_population_size;
+    pop->blocks = n / 64 + 1;
+    pop->threads = threads;
+    pop->indices = (int*)calloc((size_t)pop->size, sizeof(int));
+    pop->data = (ox_member*)calloc((size_t)pop->size, sizeof(ox_member));
+    pop->bastert = (uint64_t*)calloc((size_t)pop->blocks, sizeof(uint64_t));
+    pop->random = (uint64_t*)calloc((size_t)pop->blocks, sizeof(uint64_t));
+    pop->kappa_append = (double*)calloc((size_t)(threads > 0 ? threads : 1), sizeof(double));
+    for (int i = 0; i != pop->size; ++i)
+        pop->data[i].x = (uint64_t*)calloc((size_t)pop->blocks, sizeof(uint64_t));
+
+    for (int i = 0; i != n; ++i)
+        if (init_x(pb->maximize, pb->cost[i], 0))
+            pop->bastert[i / 64] |= (uint64_t)1 << (i % 64);
+
+    for (int i = 0, e = pop->size / 2; i != e; ++i) {
+        memcpy(pop->data[i].x, pop->bastert, sizeof(uint64_t) * (size_t)pop->blocks);
+        const double pr = clampd((double)i / (5 * e), 0.0, 1.0);
+        for (int v = 0; v != n; ++v)
+            if (ox_bernoulli(pr, &rng))
+                pop->data[i].x[v / 64] ^= (uint64_t)1 << (v % 64);
+    }
+
+    for (int i = pop->size / 2, e = pop->size; i + 1 < e; i += 2) {
+        pop_init_with_random(pop->data[i].x, &rng, n, 0.2);
+        pop_init_with_random(pop->data[i + 1].x, &rng, n, 0.8);
+        pop_pre_solve(pb, pop->data[i].x, pop->data[i + 1].x, &rng,
+                      clampd((double)i / (5 * e), 0.0, 1.0));
+    }
+
+    for (int i = 0; i != pop->size; ++i) {
+        ox_member* mb = &pop->data[i];
+        mb->hash = ox_bit_array_hash(n, mb->x);
+        mb->value = pop_results(pb, mb->x);
+        mb->remaining = pop_remaining(pb, mb->x);
+        mb->loop = 0;
+        pop->indices[i] = i;
+    }
+    pop_sort(pop);
+
+    if (rng_state)
+        *rng_state = rng;
+    return pop;
+}
+
+void
+ox_pop_destroy(ox_pop* pop)
+{
+    if (!pop)
+        return;
+    for (int i = 0; i != pop->size; ++i)
+        free(pop->data[i].x);
+    free(pop->indices);
+    free(pop->data);
+    free(pop->bastert);
+    free(pop->random);
+    free(pop->kappa_append);
+    free(pop);
+}
+
+int
+ox_pop_size(ox_pop* pop)
+{
+    return pop->size;
+}
+
+void
+ox_pop_member(ox_pop* pop, int i, uint64_t* x_words, double* value,
+              int* remaining, uint64_t* hash, int64_t* loop)
+{
+    const ox_member* mb = &pop->data[pop->indices[i]];
+    if (x_words)
+        memcpy(x_words, mb->x, sizeof(uint64_t) * (size_t)pop->blocks);
+    if (value)
+        *value = mb->value;
+    if (remaining)
+        *remaining = mb->remaining;
+    if (hash)
+        *hash = mb->hash;
+    if (loop)
+        *loop = mb->loop;
+}
+
+ox_pop_ctx*
+ox_pop_ctx_create(ox_pop* pop, unsigned thread_id, uint64_t seed)
+{
+    struct ox_pop_ctx* c = (struct ox_pop_ctx*)calloc(1, sizeof(struct ox_pop_ctx));
+    const ox_params* p = &pop->p;
+    c->rng = engine_seed(seed);
+    c->choose_sol = (ox_normal_dist){ p->init_crossover_solution_selection_mean,
+                                      p->init_crossover_solution_selection_stddev, 0.0, 0 };
+    c->variable_p = (ox_normal_dist){ p->init_mutation_variable_mean,
+                                      p->init_mutation_variable_stddev, 0.0, 0 };
+    c->value_p = (ox_normal_dist){ p->init_mutation_value_mean,
+                                   p->init_mutation_value_stddev, 0.0, 0 };
+    c->bad_lo = p->init_population_size / 5;
+    c->bad_hi = p->init_population_size - 1;
+    c->bastert_insertion = p->init_crossover_bastert_insertion;
+    c->improve_start = p->init_kappa_improve_start;
+    c->improve_increase = p->init_kappa_improve_increase;
+    c->improve_stop = p->init_kappa_improve_stop;
+    c->thread_id = thread_id;
+    return c;
+}
+
+void
+ox_pop_ctx_destroy(ox_pop_ctx* c)
+{
+    free(c);
+}
+
+uint32_t
+ox_pop_ctx_rng(ox_pop_ctx* c)
+{
+    return c->rng;
+}
+
+/* storage::choose_a_solution, itm-optimizer-common.hpp:151-160 */
+static int
+choose_a_solution(struct ox_pop* pop, struct ox_pop_ctx* c)
+{
+    double value;
+    do
+        value = ox_normal_draw(&c->choose_sol, &c->rng);
+    while (value < 0 || value > 1);
+    return (int)(pop->size * value);
+}
+
+/* storage::crossover(ctx, x, first, second), :359-371 */
+static void
+crossover_blocks(struct ox_pop* pop, struct ox_pop_ctx* c, uint64_t* x,
+                 const uint64_t* first, const uint64_t* second)
+{
+    for (int i = 0; i != pop->blocks; ++i) {
+        const uint64_t x1 = first[i], x2 = second[i];
+        x[i] = ((x1 ^ x2) & ox_uniform_u64(0, UINT64_MAX, &c->rng)) ^ x1;
+    }
+}
+
+/* storage::crossover(ctx, x), :373-421 */
+void
+ox_pop_crossover(ox_pop* pop, ox_pop_ctx* c, uint64_t* x)
+{
+    const size_t bytes = sizeof(uint64_t) * (size_t)pop->blocks;
+
+    if (ox_bernoulli(c->bastert_insertion, &c->rng)) {
+        const int first = pop->indices[choose_a_solution(pop, c)];
+        if (ox_bernoulli(0.5, &c->rng)) {
+            if (ox_bernoulli(0.5, &c->rng))
+                crossover_blocks(pop, c, x, pop->data[first].x, pop->bastert);
+            else
+                memcpy(pop->data[first].x, pop->bastert, bytes);
+        } else {
+            pop_init_with_random(pop->random, &c->rng, pop->pb->n, 0.5);
+            if (ox_bernoulli(0.5, &c->rng))
+                crossover_blocks(pop, c, x, pop->data[first].x, pop->random);
+            else
+                memcpy(pop->data[first].x, pop->random, bytes);
+        }
+    } else {
+        const int first = pop->indices[choose_a_solution(pop, c)];
+        int second = pop->indices[choose_a_solution(pop, c)];
+        while (first == second)
+            second = pop->indices[choose_a_solution(pop, c)];
+        crossover_blocks(pop, c, x, pop->data[first].x, pop->data[second].x);
+    }
+}
+
+/* best_solution_recorder::mutation, :494-526.  bit_array::set(i, bool)
+ * (bit-array.hpp:143-148) writes `val` only into bit 0 of a block and clears
+ * any other bit, whatever val is: reproduced. */
+void
+ox_pop_mutation(ox_pop* pop, ox_pop_ctx* c, uint64_t* x)
+{
+    if (c->value_p.mean == 0.0 && c->value_p.stddev == 0.0)
+        return;
+
+    double val_p, var_p;
+    do
+        var_p = ox_normal_draw(&c->variable_p, &c->rng);
+    while (var_p <= 0.0 || var_p >= 1.0);
+    do
+        val_p = ox_normal_draw(&c->value_p, &c->rng);
+    while (val_p < 0.0 || val_p > 1.0);
+
+    for (int i = 0, e = pop->pb->n; i != e; ++i) {
+        if (ox_bernoulli(var_p, &c->rng)) {
+            const uint64_t val = (uint64_t)ox_bernoulli(val_p, &c->rng);
+            const uint64_t mask = (uint64_t)1 << (i % 64);
+            uint64_t* ref = &x[i / 64];
+            *ref ^= (val ^ *ref) & mask;
+        }
+    }
+}
+
+/* best_solution_recorder::reinit, :528-554 */
+double
+ox_pop_reinit(ox_pop* pop, ox_pop_ctx* c, double kappa_min, double kappa_max,
+              uint64_t* x)
+{
+    double kappa = kappa_min;
+    double* ka = &pop->kappa_append[c->thread_id];
+
+    if (*ka < c->improve_stop) {
+        *ka += c->improve_increase;
+        kappa = kappa_min + (kappa_max - kappa_min) * *ka;
+    } else {
+        *ka = c->improve_start;
+        ox_pop_crossover(pop, c, x);
+    }
+    ox_pop_mutation(pop, c, x);
+    return kappa;
+}
+
+/* storage::insert's common part: choose_a_bad_solution, replace_result,
+ * sort (:228-300). */
+static void
+pop_replace(struct ox_pop* pop, struct ox_pop_ctx* c, const uint64_t* x,
+            double value, uint64_t hash, int64_t loop, int remaining)
+{
+    const int pos = (int)ox_uniform_u64((uint64_t)c->bad_lo, (uint64_t)c->bad_hi, &c->rng);
+    ox_member* mb = &pop->data[pop->indices[pos]];
+    memcpy(mb->x, x, sizeof(uint64_t) * (size_t)pop->blocks);
+    mb->value = value;
+    mb->hash = hash;
+    mb->loop = loop;
+    mb->remaining = remaining;
+    pop_sort(pop);
+}
+
+/* best_solution_recorder::try_update, :571-584 */
+void
+ox_pop_try_update(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x, double value,
+                  int64_t loop)
+{
+    const uint64_t hash = ox_bit_array_hash(pop->pb->n, x);
+    for (int i = 0; i != pop->size; ++i)
+        if (pop->data[i].remaining == 0 && pop->data[i].value == value &&
+            pop->data[i].hash == hash)
+            return;
+    pop_replace(pop, c, x, value, hash, loop, 0);
+}
+
+/* best_solution_recorder::try_advance, :556-569 */
+void
+ox_pop_try_advance(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x, int remaining,
+                   int64_t loop)
+{
+    const uint64_t hash = ox_bit_array_hash(pop->pb->n, x);
+    for (int i = 0; i != pop->size; ++i)
+        if (pop->data[i].remaining == remaining && pop->data[i].hash == hash)
+            return;
+    pop_replace(pop, c, x, pop_results(pop->pb, x), hash, loop, remaining);
+}

@@ -167,6 +167,31 @@ int ox_bb_solve(int maximize, double* value, int* factor, int* id, int n,
 int ox_exhaustive_solve(int maximize, const int* cst_factor, double* value,
                         int* factor, int* id, int n, int bmin, int bmax);
 
+/* ---- optimizer population ------------------------------
+ * local_context, storage and best_solution_recorder of
+ * lib/src/itm-optimizer-common.hpp:52-594.  `p` must be clamped. */
+typedef struct ox_pop ox_pop;
+typedef struct ox_pop_ctx ox_pop_ctx;
+ox_pop* ox_pop_create(ox_problem* pb, const ox_params* p, uint64_t master_seed,
+                      int threads, uint32_t* rng_state);
+void ox_pop_destroy(ox_pop* pop);
+int ox_pop_size(ox_pop* pop);
+/* member at sorted position i (storage::get_best(i)) */
+void ox_pop_member(ox_pop* pop, int i, uint64_t* x_words, double* value,
+                   int* remaining, uint64_t* hash, int64_t* loop);
+ox_pop_ctx* ox_pop_ctx_create(ox_pop* pop, unsigned thread_id, uint64_t seed);
+void ox_pop_ctx_destroy(ox_pop_ctx* c);
+uint32_t ox_pop_ctx_rng(ox_pop_ctx* c);
+double ox_pop_reinit(ox_pop* pop, ox_pop_ctx* c, double kappa_min,
+                     double kappa_max, uint64_t* x_words);
+void ox_pop_mutation(ox_pop* pop, ox_pop_ctx* c, uint64_t* x_words);
+void ox_pop_crossover(ox_pop* pop, ox_pop_ctx* c, uint64_t* x_words);
+void ox_pop_try_update(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x_words,
+                       double value, int64_t loop);
+void ox_pop_try_advance(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x_words,
+                        int remaining, int64_t loop);
+uint64_t ox_bit_array_hash(int n, const uint64_t* x_words);
+
 #ifdef __cplusplus
 }
 #endif

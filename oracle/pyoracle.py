@@ -331,6 +331,7 @@ def ref(fast: bool = False):
     lib.bxref_std_uniform_u64.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
     lib.bxref_std_uniform_u64.restype = C.c_uint64
     lib.bxref_std_normal.argtypes = [C.c_double, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32)]
+    lib.bxref_generate_seed.argtypes = [C.c_uint64, C.c_uint, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
     lib.bxref_std_pow.argtypes = [C.c_double, C.c_double]
     lib.bxref_std_pow.restype = C.c_double
     lib.bxref_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
@@ -437,4 +438,110 @@ class RefRun(_RunBase):
     def close(self):
         if self.h:
             self.lib.bxref_run_end(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------
+# optimizer population: the same Python face over the
+# compiled reference (prefix bxref_pop_) and the C restatement (prefix ox_pop_)
+# --------------------------------------------------------------------------
+_u64arr = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+def _bind_population(lib, pre, hash_name):
+    if getattr(lib, "_pop_bound", False):
+        return
+    f = lambda name: getattr(lib, pre + name)
+    f("create").restype = C.c_void_p
+    f("destroy").argtypes = [C.c_void_p]
+    f("size").argtypes = [C.c_void_p]
+    f("member").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                            C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+    f("ctx_create").argtypes = [C.c_void_p, C.c_uint, C.c_uint64]
+    f("ctx_create").restype = C.c_void_p
+    f("ctx_destroy").argtypes = [C.c_void_p]
+    f("ctx_rng").argtypes = [C.c_void_p]
+    f("ctx_rng").restype = C.c_uint32
+    f("reinit").argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, _u64arr]
+    f("reinit").restype = C.c_double
+    f("mutation").argtypes = [C.c_void_p, C.c_void_p, _u64arr]
+    f("crossover").argtypes = [C.c_void_p, C.c_void_p, _u64arr]
+    f("try_update").argtypes = [C.c_void_p, C.c_void_p, _u64arr, C.c_double, C.c_int64]
+    f("try_advance").argtypes = [C.c_void_p, C.c_void_p, _u64arr, C.c_int, C.c_int64]
+    h = getattr(lib, hash_name)
+    h.argtypes = [C.c_int, _u64arr]
+    h.restype = C.c_uint64
+    lib._pop_bound = True
+
+
+class Population:
+    """best_solution_recorder + local_contexts (itm-optimizer-common.hpp:52-594)."""
+
+    def __init__(self, problem, master_seed: int, threads: int = 1, params: Params | None = None):
+        self.n = problem.n
+        self.words = self.n // 64 + 1
+        rng = C.c_uint32()
+        if isinstance(problem, RefProblem):
+            self.lib, self.pre, hn = problem.lib, "bxref_pop_", "bxref_bit_array_hash"
+            _bind_population(self.lib, self.pre, hn)
+            self.lib.bxref_pop_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint32)]
+            self.h = self.lib.bxref_pop_create(problem.h, master_seed, threads, C.byref(rng))
+        else:
+            self.lib, self.pre, hn = problem.lib, "ox_pop_", "ox_bit_array_hash"
+            _bind_population(self.lib, self.pre, hn)
+            self.lib.ox_pop_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint64, C.c_int,
+                                               C.POINTER(C.c_uint32)]
+            self.h = self.lib.ox_pop_create(problem.h, C.byref(params), master_seed, threads, C.byref(rng))
+        self._hash = getattr(self.lib, hn)
+        self.rng_after_ctor = rng.value
+        self.ctxs = {}
+
+    def _f(self, name):
+        return getattr(self.lib, self.pre + name)
+
+    def size(self) -> int:
+        return self._f("size")(self.h)
+
+    def member(self, i: int):
+        x = np.zeros(self.words, np.uint64)
+        v, r, h, l = C.c_double(), C.c_int(), C.c_uint64(), C.c_int64()
+        self._f("member")(self.h, i, x.ctypes.data_as(C.c_void_p), C.byref(v), C.byref(r), C.byref(h),
+                          C.byref(l))
+        return {"x": x, "value": v.value, "remaining": r.value, "hash": h.value, "loop": l.value}
+
+    def members(self):
+        return [self.member(i) for i in range(self.size())]
+
+    def ctx(self, thread_id: int, seed: int):
+        c = self._f("ctx_create")(self.h, thread_id, seed)
+        self.ctxs[thread_id] = c
+        return c
+
+    def ctx_rng(self, thread_id: int) -> int:
+        return self._f("ctx_rng")(self.ctxs[thread_id])
+
+    def reinit(self, thread_id: int, kappa_min: float, kappa_max: float, x: np.ndarray) -> float:
+        return self._f("reinit")(self.h, self.ctxs[thread_id], kappa_min, kappa_max, x)
+
+    def mutation(self, thread_id: int, x: np.ndarray):
+        self._f("mutation")(self.h, self.ctxs[thread_id], x)
+
+    def crossover(self, thread_id: int, x: np.ndarray):
+        self._f("crossover")(self.h, self.ctxs[thread_id], x)
+
+    def try_update(self, thread_id: int, x: np.ndarray, value: float, loop: int):
+        self._f("try_update")(self.h, self.ctxs[thread_id], x, value, loop)
+
+    def try_advance(self, thread_id: int, x: np.ndarray, remaining: int, loop: int):
+        self._f("try_advance")(self.h, self.ctxs[thread_id], x, remaining, loop)
+
+    def hash(self, x: np.ndarray) -> int:
+        return self._hash(self.n, x)
+
+    def close(self):
+        for c in self.ctxs.values():
+            self._f("ctx_destroy")(c)
+        self.ctxs = {}
+        if self.h:
+            self._f("destroy")(self.h)
             self.h = None

@@ -118,6 +118,8 @@ uint64_t bxref_std_uniform_u64(uint64_t a, uint64_t b, uint32_t* rng_state);
 void bxref_std_normal(double mean, double stddev, int count, double* out,
                       uint32_t* rng_state);
 double bxref_std_pow(double a, double b);
+/* generate_seed (itm-common.hpp:1457-1484) from random_engine(master_seed). */
+void bxref_generate_seed(uint64_t master_seed, unsigned count, uint64_t* out);
 /* Sub-solver known-answer access (lib/test/lib.cpp:376-563). */
 int bxref_bb_solve(int maximize, double* value, int* factor, int* id, int n,
                    int bmin, int bmax);

@@ -576,6 +576,15 @@ bxref_std_normal(double mean,
     *rng_state = bxref::rng_state_of(rng);
 }
 
+void
+bxref_generate_seed(uint64_t master_seed, unsigned count, uint64_t* out)
+{
+    random_engine rng(static_cast<random_engine::result_type>(master_seed));
+    auto seeds = itm::generate_seed(rng, count);
+    for (unsigned i = 0; i != count; ++i)
+        out[i] = seeds[i];
+}
+
 double
 bxref_std_pow(double a, double b)
 {
