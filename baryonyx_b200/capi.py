@@ -71,6 +71,11 @@ EXPORTS = [
     "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
     "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_launches",
     "bxg_batch_words32", "bxg_batch_begin_device",
+    "bxg_population_create", "bxg_population_destroy", "bxg_population_size",
+    "bxg_population_master_state", "bxg_population_member", "bxg_population_worker_seed",
+    "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
+    "bxg_population_mutation", "bxg_population_try_update", "bxg_population_try_advance",
+    "bxg_population_score", "bxg_optimize_round", "bxg_bit_array_hash",
 ]
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -91,12 +96,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BXG_LIB", LIB_PATH)  # BXG_LIB: experiment builds of the same ABI
+    if not os.path.exists(path):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m baryonyx_b200.build` "
             "(nvcc, sm_100a).  There is no CPU fallback."
         )
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.bxg_last_error.restype = C.c_char_p
     L.bxg_default_params.argtypes = [C.POINTER(Params)]
     L.bxg_default_params.restype = None
@@ -301,4 +307,113 @@ class Batch:
     def close(self):
         if self.h:
             lib().bxg_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+def _bind_population(L):
+    if getattr(L, "_pop_bound", False):
+        return
+    L.bxg_population_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint64, C.c_int,
+                                        C.POINTER(C.c_void_p)]
+    L.bxg_population_destroy.argtypes = [C.c_void_p]
+    L.bxg_population_size.argtypes = [C.c_void_p]
+    L.bxg_population_master_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.bxg_population_member.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+    L.bxg_population_worker_seed.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    L.bxg_population_worker_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.bxg_population_reinit.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _u64p,
+                                        C.POINTER(C.c_double)]
+    L.bxg_population_crossover.argtypes = [C.c_void_p, C.c_int, _u64p]
+    L.bxg_population_mutation.argtypes = [C.c_void_p, C.c_int, _u64p]
+    L.bxg_population_try_update.argtypes = [C.c_void_p, C.c_int, _u64p, C.c_double, C.c_int64]
+    L.bxg_population_try_advance.argtypes = [C.c_void_p, C.c_int, _u64p, C.c_int, C.c_int64]
+    L.bxg_population_score.argtypes = [C.c_void_p, _u64p, C.c_int, _i32p, _f64p]
+    L.bxg_optimize_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bxg_bit_array_hash.argtypes = [C.c_int, _u64p]
+    L.bxg_bit_array_hash.restype = C.c_uint64
+    L._pop_bound = True
+
+
+class Population:
+    """bxg_population: the optimizer's candidate vectors and per-worker random
+    streams (best_solution_recorder / local_context of the reference)."""
+
+    def __init__(self, pb: Problem, params: Params, master_seed: int, workers: int = 1):
+        _bind_population(lib())
+        self.pb = pb
+        self.n = pb.n
+        self.words = pb.n // 64 + 1
+        self.h = C.c_void_p()
+        check(lib().bxg_population_create(pb.h, C.byref(params), master_seed, workers, C.byref(self.h)))
+        st = C.c_uint32()
+        check(lib().bxg_population_master_state(self.h, C.byref(st)))
+        self.rng_after_ctor = st.value
+
+    def size(self) -> int:
+        return lib().bxg_population_size(self.h)
+
+    def member(self, i: int):
+        x = np.zeros(self.words, np.uint64)
+        v, r, h, l = C.c_double(), C.c_int(), C.c_uint64(), C.c_int64()
+        check(lib().bxg_population_member(self.h, i, x.ctypes.data_as(C.c_void_p), C.byref(v), C.byref(r),
+                                          C.byref(h), C.byref(l)))
+        return {"x": x, "value": v.value, "remaining": r.value, "hash": h.value, "loop": l.value}
+
+    def members(self):
+        return [self.member(i) for i in range(self.size())]
+
+    def ctx(self, worker: int, seed: int):
+        check(lib().bxg_population_worker_seed(self.h, worker, seed))
+
+    def ctx_rng(self, worker: int) -> int:
+        st = C.c_uint32()
+        check(lib().bxg_population_worker_state(self.h, worker, C.cast(C.byref(st), C.c_void_p), None))
+        return st.value
+
+    def set_ctx_rng(self, worker: int, state: int):
+        st = C.c_uint32(state)
+        check(lib().bxg_population_worker_state(self.h, worker, None, C.cast(C.byref(st), C.c_void_p)))
+
+    def reinit(self, worker: int, kappa_min: float, kappa_max: float, x: np.ndarray) -> float:
+        k = C.c_double()
+        check(lib().bxg_population_reinit(self.h, worker, kappa_min, kappa_max, x, C.byref(k)))
+        return k.value
+
+    def crossover(self, worker: int, x: np.ndarray):
+        check(lib().bxg_population_crossover(self.h, worker, x))
+
+    def mutation(self, worker: int, x: np.ndarray):
+        check(lib().bxg_population_mutation(self.h, worker, x))
+
+    def try_update(self, worker: int, x: np.ndarray, value: float, loop: int):
+        check(lib().bxg_population_try_update(self.h, worker, x, value, loop))
+
+    def try_advance(self, worker: int, x: np.ndarray, remaining: int, loop: int):
+        check(lib().bxg_population_try_advance(self.h, worker, x, remaining, loop))
+
+    def score(self, xs: np.ndarray):
+        xs = np.ascontiguousarray(xs, np.uint64).reshape(-1, self.words)
+        rem = np.zeros(len(xs), np.int32)
+        val = np.zeros(len(xs), np.float64)
+        check(lib().bxg_population_score(self.h, xs.reshape(-1), len(xs), rem, val))
+        return rem, val
+
+    def optimize_round(self, batch: "Batch", first_round: bool):
+        """One optimizer call on every lane of `batch` (lane l = worker l)."""
+        st = np.zeros(batch.n_lanes, np.int32)
+        val = np.zeros(batch.n_lanes, np.float64)
+        rem = np.zeros(batch.n_lanes, np.int32)
+        check(lib().bxg_optimize_round(batch.h, self.h, int(first_round), _ptr(st), _ptr(val), _ptr(rem)))
+        return {"status": st, "value": val, "remaining": rem}
+
+    def hash(self, x: np.ndarray) -> int:
+        return lib().bxg_bit_array_hash(self.n, x)
+
+    def close(self):
+        if self.h:
+            lib().bxg_population_destroy(self.h)
             self.h = C.c_void_p()

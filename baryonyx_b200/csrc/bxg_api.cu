@@ -1408,3 +1408,5 @@ bxg_batch_launches(bxg_batch* b, int64_t* launches)
 }
 
 } // extern "C"
+
+#include "bxg_population.cuh"

@@ -42,6 +42,10 @@ namespace {
 
 constexpr int kFam = BXG_FAM;
 
+#ifndef BXG_GATHER_UNROLL
+#define BXG_GATHER_UNROLL 4
+#endif
+
 // The CTA's dynamic shared memory: [Lane][Shared][row scratch][R values][pi]
 // [activities][x].  Views built from this symbol keep their address space, so
 // the hot path compiles to LDS/STS/ATOMS instead of generic accesses.
@@ -637,6 +641,7 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     Lane& L = the_lane();
     const int tid = threadIdx.x, T = blockDim.x;
     const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    Shared* const sh = the_shared();
     const RowHdr hdr = L.row_hdr[k];
     const int r0 = hdr.r0;
     const int r_size = hdr.r_size;
@@ -653,7 +658,6 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
     double* const pown = view<SM>(L.pown, L.o_pown);
     double* const gP = L.P;
-    Shared* const sh = the_shared();
     const int2* __restrict__ gp = L.gp + hdr.g0;
     const int S = hdr.S;
     const int bkmin = hdr.bmin, bkmax = hdr.bmax;
@@ -669,7 +673,6 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     if (k_next >= 0)
         nh = *reinterpret_cast<const int2*>(L.row_hdr + k_next);
     int4 ni = make_int4(0, 0, 0, 0);
-
     int odd = 0;    // NaN or -0.0 seen by this thread
     int counts = 0; // low half: values that neither stop the scan nor are zero; high half: zeros
     // candidates of this thread: the two smallest keys (ca <= cb); for an
@@ -677,11 +680,43 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     // the smallest stopping key (sb)
     unsigned long long ca = ~0ull, cb = ~0ull, sa = ~0ull, sb = ~0ull;
 
+// @region update_row.finish
+    // What both gathers end with for element i of the row: the reduced cost
+    // from the two column sums (compute_reduced_costs' last line), the push
+    // term, and this thread's share of the selection reductions.
+    auto finish = [&](int i, double cj, double sum_pi, double sum_p, double own) {
+        double v = __dsub_rn(__dsub_rn(cj, sum_pi), sum_p);
+        if (FAM != FAM_01 && L.row_a[r0 + i] < 0) {
+            v = -v;
+            own = -own;
+        }
+        if (push)
+            v = __dadd_rn(v, __dmul_rn(obj_amp, FAM == FAM_01 ? cost[i] : cj));
+
+        if (v != v || (v == 0.0 && __double_as_longlong(v) < 0))
+            odd = 1;
+        const bool stop = maximize ? v < 0 : v > 0;
+        const unsigned long long key = key_of(v, maximize);
+        merge_min2(ca, cb, key, ~0ull);
+        if (!is_eq) {
+            if (v == 0.0)
+                counts += 1 << 16;
+            else if (!stop)
+                counts += 1;
+            if (stop)
+                sb = key < sb ? key : sb;
+            else
+                sa = ~key < sa ? ~key : sa;
+        }
+        key0[i] = (unsigned long long)__double_as_longlong(v);
+        pown[i] = own;
+    };
+
 // @region update_row.chunk
     for (int ia = 0; ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
         int ib = r_size;
-        const int fa = row_eptr[r0 + ia];
+        const int fa = ia == 0 ? 0 : row_eptr[r0 + ia];
         int fb = S;
         if (S - fa > stage_cap) {
             int lo = ia + 1, hi = r_size; // last ib with eptr[ib] - fa <= cap
@@ -700,19 +735,20 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         // stage 1: entries.  The index is clamped rather than predicated, so
         // the loads of a trip are unconditional and independent.
         const int g_last = fb - 1;
-        for (int g = fa + tid; g < fb; g += 4 * T) {
-            int2 e[4];
-            double p[4];
+        constexpr int U = BXG_GATHER_UNROLL; // independent (entry, P) load pairs per thread and trip
+        for (int g = fa + tid; g < fb; g += U * T) {
+            int2 e[U];
+            double p[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int gg = g + u * T;
                 e[u] = gp[gg < g_last ? gg : g_last];
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < U; ++u)
                 p[u] = gP[e[u].x];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int gg = g + u * T;
                 const int rs = e[u].y;
                 double a_pi = s_pi[rs >> 1];
@@ -736,56 +772,19 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
             t_gather = clock64();
 
 // @region update_row.stage2
-        // stage 2: elements.  A thread owns elements i and i + T of the chunk
-        // and fetches what both need before summing either, so a row a little
-        // longer than the CTA does not pay the load latency twice.
-        auto element = [&](int i, const int4 info, int eptr, double cj) {
-            const double2* const c = st + (eptr - fa);
+        // stage 2: elements, each adding its column's terms left to right
+        for (int i = ia + tid; i < ib; i += T) {
+            const int4 info = row_info[r0 + i]; // c0, c1, own CSC position, column
+            const double2* const c = st + (row_eptr[r0 + i] - fa);
             const int len = info.y - info.x;
+            const double cj = cost[info.w];
             double sum_pi = 0.0, sum_p = 0.0;
             for (int t = 0; t < len; ++t) {
                 const double2 term = c[t];
                 sum_pi = __dadd_rn(sum_pi, term.y);
                 sum_p = __dadd_rn(sum_p, term.x);
             }
-            double own = c[info.z - info.x].x;
-            double v = __dsub_rn(__dsub_rn(cj, sum_pi), sum_p);
-            if (FAM != FAM_01 && L.row_a[r0 + i] < 0) {
-                v = -v;
-                own = -own;
-            }
-            if (push)
-                v = __dadd_rn(v, __dmul_rn(obj_amp, FAM == FAM_01 ? cost[i] : cj));
-
-            if (v != v || (v == 0.0 && __double_as_longlong(v) < 0))
-                odd = 1;
-            const bool stop = maximize ? v < 0 : v > 0;
-            const unsigned long long key = key_of(v, maximize);
-            merge_min2(ca, cb, key, ~0ull);
-            if (!is_eq) {
-                if (v == 0.0)
-                    counts += 1 << 16;
-                else if (!stop)
-                    counts += 1;
-                if (stop)
-                    sb = key < sb ? key : sb;
-                else
-                    sa = ~key < sa ? ~key : sa;
-            }
-            key0[i] = (unsigned long long)__double_as_longlong(v);
-            pown[i] = own;
-        };
-        for (int i = ia + tid; i < ib; i += 2 * T) {
-            const int i2 = i + T < ib ? i + T : i;
-            const int4 info1 = row_info[r0 + i];
-            const int4 info2 = row_info[r0 + i2];
-            const int eptr1 = row_eptr[r0 + i];
-            const int eptr2 = row_eptr[r0 + i2];
-            const double cj1 = cost[info1.w];
-            const double cj2 = cost[info2.w];
-            element(i, info1, eptr1, cj1);
-            if (i2 != i)
-                element(i2, info2, eptr2, cj2);
+            finish(i, cj, sum_pi, sum_p, c[info.z - info.x].x);
         }
         ia = ib;
         if (ia < r_size)
@@ -964,19 +963,11 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
                     sh->pi_changed = 1;
             }
 // @region update_row.fastD
-            for (int i = tid; i < r_size; i += 2 * T) {
-                const int i2 = i + T < r_size ? i + T : i;
-                const int4 info1 = row_info[r0 + i];
-                const int4 info2 = row_info[r0 + i2];
-                const unsigned long long key1 =
+            for (int i = tid; i < r_size; i += T) {
+                const int4 info = row_info[r0 + i];
+                const unsigned long long key =
                   key_of(__longlong_as_double((long long)key0[i]), maximize);
-                affect_element<FAM, SM>(L, r0, i, info1, pown[i], selected >= 0 && key1 <= key_sel, d);
-                if (i2 != i) {
-                    const unsigned long long key2 =
-                      key_of(__longlong_as_double((long long)key0[i2]), maximize);
-                    affect_element<FAM, SM>(L, r0, i2, info2, pown[i2],
-                                            selected >= 0 && key2 <= key_sel, d);
-                }
+                affect_element<FAM, SM>(L, r0, i, info, pown[i], selected >= 0 && key <= key_sel, d);
             }
             __syncthreads();
             if (tid == 0) {
@@ -1895,7 +1886,7 @@ store_best(Lane& L, const DevBatch& b, int lane_id, bool by_value, double value,
 template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
-        const __grid_constant__ DevBatch b, SmemPlan plan)
+        const __grid_constant__ DevBatch b, SmemPlan plan, int optimizer)
 {
     const int lane_id = blockIdx.x;
     Lists ls;
@@ -1910,7 +1901,13 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
 
     const long w_limit = (long)pr.w;
     bool start_push = false;
-    double kappa = pr.kappa_min;
+    // optimizer = 1: one call of a worker of optimize_functor::operator()
+    // (itm-optimizer-common.hpp:658-750) instead of solver_functor's run: the
+    // restart begins at the kappa best_solution_recorder::reinit returned, the
+    // push sweep runs at kappa = pushing_k_factor and every push restarts the
+    // schedule from that kappa
+    const double kappa_start = optimizer ? b.kappa[lane_id] : pr.kappa_min;
+    double kappa = kappa_start;
 
     for (long long i = 0; i != pr.limit; ++i) {
         const int remaining = order_run(L, ls, kappa, 0, 0.0);
@@ -1944,8 +1941,8 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
     } else {
         for (int push = 0; push < pr.pushes_limit; ++push) {
             int remaining =
-              order_run(L, ls, __dmul_rn(pr.pushing_k_factor, kappa), 1,
-                        pr.pushing_objective_amplifier);
+              order_run(L, ls, optimizer ? pr.pushing_k_factor : __dmul_rn(pr.pushing_k_factor, kappa),
+                        1, pr.pushing_objective_amplifier);
 
             if (remaining == 0) {
                 const double v = objective(L);
@@ -1954,6 +1951,8 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
                            m_best_remaining, m_best_value, m_best_loop, m_best_has_x);
             }
 
+            if (optimizer)
+                kappa = kappa_start;
             for (int iter = 0; iter < pr.pushing_iteration_limit; ++iter) {
                 remaining = order_run(L, ls, kappa, 0, 0.0);
 
@@ -2198,10 +2197,10 @@ BXG_FAM_FN(launch_sweep)(const DevProblem& pb, const DevParams& pr, const DevBat
 
 void
 BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
-             const LaunchCfg& cfg, cudaStream_t s)
+             const LaunchCfg& cfg, cudaStream_t s, int optimizer)
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
-    BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan);
+    BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan, optimizer);
 }
 
 void

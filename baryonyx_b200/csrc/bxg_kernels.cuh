@@ -181,7 +181,7 @@ size_t z_scratch_bytes(int max_zrow);
     void launch_sweep_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
                            int push, double obj_amp, const LaunchCfg& cfg, cudaStream_t s);      \
     void launch_solve_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
-                           const LaunchCfg& cfg, cudaStream_t s);                                \
+                           const LaunchCfg& cfg, cudaStream_t s, int optimizer);                 \
     void launch_objective_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,     \
                                const LaunchCfg& cfg, cudaStream_t s);
 BXG_DECLARE_FAMILY(0)
@@ -224,9 +224,9 @@ launch_sweep(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int p
 
 inline void
 launch_solve(const DevProblem& pb, const DevParams& pr, const DevBatch& b, const LaunchCfg& cfg,
-             cudaStream_t s)
+             cudaStream_t s, int optimizer = 0)
 {
-    BXG_BY_FAMILY(pb, launch_solve, pb, pr, b, cfg, s);
+    BXG_BY_FAMILY(pb, launch_solve, pb, pr, b, cfg, s, optimizer);
 }
 
 inline void

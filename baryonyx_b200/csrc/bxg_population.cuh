@@ -1,0 +1,703 @@
+// bxg_population.cuh -- the optimizer's population behind the C ABI
+// (bxg_population_*, include/bxg.h).  Included at the end of bxg_api.cu.
+//
+// What the reference keeps in best_solution_recorder / storage / local_context
+// (lib/src/itm-optimizer-common.hpp:52-594): `size` candidate vectors ordered by
+// (remaining constraints, objective), and per worker an engine plus the
+// distributions that pick parents, mutation rates and the member to replace.
+// It is scalar, strictly sequential work on one random stream per worker, so
+// it runs on the host -- with the standard library's engine and distributions,
+// exactly like the reference, which is what makes the streams identical -- and
+// only the bulk part runs on the device: scoring many vectors against the
+// constraint matrix (k_score_vectors).  The lanes of a batch are the workers.
+#ifndef BXG_POPULATION_CUH
+#define BXG_POPULATION_CUH
+
+namespace {
+
+// remaining constraints and objective of `count` vectors; one CTA per vector.
+// x: [count][words] 64-bit blocks (bit_array layout, bit-array.hpp:60-66).
+// Raw merged-constraint bounds, as storage's constructor uses them
+// (itm-optimizer-common.hpp:205-219).
+__global__ void __launch_bounds__(256)
+k_score_vectors(const __grid_constant__ DevProblem pb, const int* __restrict__ cmin,
+                const int* __restrict__ cmax, const unsigned long long* __restrict__ x, int words,
+                int* __restrict__ remaining, double* __restrict__ value)
+{
+    const unsigned long long* xv = x + (size_t)blockIdx.x * words;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    __shared__ int s_bad[32];
+    __shared__ double s_val[32];
+
+    auto bit = [&](int i) { return (int)((xv[i >> 6] >> (i & 63)) & 1ull); };
+
+    int bad = 0;
+    for (int k = warp; k < pb.m; k += nwarps) {
+        int v = 0;
+        for (int e = pb.row_ptr[k] + lane; e < pb.row_ptr[k + 1]; e += 32)
+            v += (pb.row_a ? pb.row_a[e] : 1) * bit(pb.row_col[e]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && !(cmin[k] <= v && v <= cmax[k]))
+            ++bad;
+    }
+    if (lane == 0)
+        s_bad[warp] = bad;
+
+    // default_cost_type::results (itm-common.hpp:1140-1147) adds in element
+    // order; any order gives the same double when the sums are exact
+    double part = 0.0;
+    if (pb.obj_any_order) {
+        for (int i = tid; i < pb.n_obj; i += T)
+            if (bit(pb.obj_var[i]))
+                part += pb.obj_factor[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0)
+            s_val[warp] = part;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int w = 0; w < nwarps; ++w)
+            total += s_bad[w];
+        remaining[blockIdx.x] = total;
+        double v = pb.cost_constant;
+        if (pb.obj_any_order) {
+            for (int w = 0; w < nwarps; ++w)
+                v += s_val[w];
+        } else {
+            for (int i = 0; i < pb.n_obj; ++i)
+                if (bit(pb.obj_var[i]))
+                    v = __dadd_rn(v, pb.obj_factor[i]);
+        }
+        value[blockIdx.x] = v;
+    }
+}
+
+using engine_t = std::default_random_engine;
+
+uint32_t
+engine_state(const engine_t& e)
+{
+    // minstd_rand0 streams its state as a decimal number
+    std::ostringstream os;
+    os << e;
+    return static_cast<uint32_t>(std::stoul(os.str()));
+}
+
+void
+engine_set_state(engine_t& e, uint32_t state)
+{
+    std::istringstream is(std::to_string(state));
+    is >> e;
+}
+
+} // namespace
+
+struct bxg_population
+{
+    struct member
+    {
+        std::vector<uint64_t> x;
+        double value = 0;
+        uint64_t hash = 0;
+        int64_t loop = 0;
+        int remaining = 0;
+    };
+
+    // local_context, itm-optimizer-common.hpp:52-92
+    struct worker
+    {
+        engine_t rng;
+        std::normal_distribution<double> parent;
+        std::normal_distribution<double> mutation_rate;
+        std::normal_distribution<double> mutation_value;
+        std::uniform_int_distribution<int> victim;
+        std::uniform_int_distribution<std::size_t> mask;
+        std::bernoulli_distribution special_parent;
+        double improve = 0; // m_kappa_append[thread_id]
+        bool seeded = false;
+    };
+
+    bxg_problem* pb = nullptr;
+    bxg_params p{};
+    int size = 0, words = 0;
+    engine_t master;
+    std::vector<int> order; // m_indices
+    std::vector<member> data;
+    std::vector<uint64_t> bastert, scratch;
+    std::vector<worker> workers;
+    DevBuf<int> d_cmin, d_cmax, d_remaining;
+    DevBuf<unsigned long long> d_x;
+    DevBuf<double> d_value;
+
+    bool maximize() const { return pb->maximize != 0; }
+
+    bool better(double l, double r) const { return maximize() ? l > r : l < r; }
+
+    static uint64_t hash_of(const uint64_t* x, int words)
+    {
+        // bit_array_hash, bit-array.hpp:410-423; std::hash<size_t> is the identity
+        uint64_t h = 0;
+        for (int i = 0; i != words; ++i)
+            h ^= x[i] + 0x9e3779b9u + (h << 6) + (h >> 2);
+        return h;
+    }
+
+    double objective(const uint64_t* x) const
+    {
+        double v = pb->cost_constant;
+        for (size_t i = 0; i != pb->obj_var.size(); ++i)
+            if ((x[pb->obj_var[i] >> 6] >> (pb->obj_var[i] & 63)) & 1u)
+                v += pb->obj_factor[i];
+        return v;
+    }
+
+    // storage::sort, itm-optimizer-common.hpp:423-441
+    void sort()
+    {
+        std::sort(order.begin(), order.end(), [this](int a, int b) {
+            const member &l = data[a], &r = data[b];
+            if (l.remaining != r.remaining)
+                return l.remaining < r.remaining;
+            return better(l.value, r.value);
+        });
+    }
+
+    // remaining constraints and objective of `count` vectors on the device
+    int score(const uint64_t* x, int count, int* remaining, double* value)
+    {
+        if (count <= 0)
+            return BXG_OK;
+        CUDA_TRY(cudaSetDevice(pb->device));
+        const size_t n = static_cast<size_t>(count) * words;
+        if (d_x.n < n) {
+            if (d_x.p)
+                cudaFree(d_x.p);
+            d_x.p = nullptr;
+            CUDA_TRY(d_x.alloc(n));
+        }
+        if (d_remaining.n < static_cast<size_t>(count)) {
+            if (d_remaining.p)
+                cudaFree(d_remaining.p);
+            if (d_value.p)
+                cudaFree(d_value.p);
+            d_remaining.p = nullptr;
+            d_value.p = nullptr;
+            CUDA_TRY(d_remaining.alloc(count));
+            CUDA_TRY(d_value.alloc(count));
+        }
+        CUDA_TRY(cudaMemcpy(d_x.p, x, sizeof(uint64_t) * n, cudaMemcpyHostToDevice));
+        k_score_vectors<<<count, 256>>>(pb->dev, d_cmin.p, d_cmax.p, d_x.p, words, d_remaining.p,
+                                        d_value.p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(remaining, d_remaining.p, sizeof(int) * count, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(value, d_value.p, sizeof(double) * count, cudaMemcpyDeviceToHost));
+        return BXG_OK;
+    }
+
+    // storage::choose_a_solution, :151-160
+    int pick_parent(worker& w)
+    {
+        double v;
+        do
+            v = w.parent(w.rng);
+        while (v < 0 || v > 1);
+        return static_cast<int>(size * v);
+    }
+
+    // storage::crossover(ctx, x, first, second), :359-371
+    void mix(worker& w, uint64_t* x, const uint64_t* a, const uint64_t* b)
+    {
+        for (int i = 0; i != words; ++i)
+            x[i] = ((a[i] ^ b[i]) & w.mask(w.rng)) ^ a[i];
+    }
+
+    // storage::crossover(ctx, x), :373-421
+    void crossover(worker& w, uint64_t* x)
+    {
+        if (w.special_parent(w.rng)) {
+            member& first = data[order[pick_parent(w)]];
+            std::bernoulli_distribution coin(0.5);
+            const bool use_bastert = coin(w.rng);
+            if (!use_bastert) {
+                // init_with_random(m_random, rng, n, 0.5), itm-common.hpp:269-282
+                std::bernoulli_distribution half(0.5);
+                for (int i = 0; i != pb->n; ++i) {
+                    const uint64_t bit = uint64_t{ 1 } << (i & 63);
+                    if (half(w.rng))
+                        scratch[i >> 6] |= bit;
+                    else
+                        scratch[i >> 6] &= ~bit;
+                }
+            }
+            const std::vector<uint64_t>& other = use_bastert ? bastert : scratch;
+            if (coin(w.rng))
+                mix(w, x, first.x.data(), other.data());
+            else
+                first.x = other; // the member's value and hash stay as they were (:389,402)
+        } else {
+            const int first = order[pick_parent(w)];
+            int second = order[pick_parent(w)];
+            while (first == second)
+                second = order[pick_parent(w)];
+            mix(w, x, data[first].x.data(), data[second].x.data());
+        }
+    }
+
+    // best_solution_recorder::mutation, :494-526
+    void mutation(worker& w, uint64_t* x)
+    {
+        if (w.mutation_value.mean() == 0.0 && w.mutation_value.stddev() == 0.0)
+            return;
+        double rate, ones;
+        do
+            rate = w.mutation_rate(w.rng);
+        while (rate <= 0.0 || rate >= 1.0);
+        do
+            ones = w.mutation_value(w.rng);
+        while (ones < 0.0 || ones > 1.0);
+
+        std::bernoulli_distribution hit(rate), one(ones);
+        for (int i = 0; i != pb->n; ++i) {
+            if (!hit(w.rng))
+                continue;
+            // bit_array::set(i, bool), bit-array.hpp:143-148: the value lands
+            // in bit 0 of the block only; any other bit is cleared
+            const uint64_t val = one(w.rng) ? 1u : 0u;
+            const uint64_t bit = uint64_t{ 1 } << (i & 63);
+            uint64_t& ref = x[i >> 6];
+            ref ^= (val ^ ref) & bit;
+        }
+    }
+
+    // best_solution_recorder::reinit, :528-554
+    double reinit(worker& w, double kappa_min, double kappa_max, uint64_t* x)
+    {
+        double kappa = kappa_min;
+        if (w.improve < p.init_kappa_improve_stop) {
+            w.improve += p.init_kappa_improve_increase;
+            kappa = kappa_min + (kappa_max - kappa_min) * w.improve;
+        } else {
+            w.improve = p.init_kappa_improve_start;
+            crossover(w, x);
+        }
+        mutation(w, x);
+        return kappa;
+    }
+
+    // storage::insert, :228-300: the victim comes from the worst four fifths
+    void replace(worker& w, const uint64_t* x, double value, uint64_t hash, int64_t loop,
+                 int remaining)
+    {
+        member& mb = data[order[w.victim(w.rng)]];
+        mb.x.assign(x, x + words);
+        mb.value = value;
+        mb.hash = hash;
+        mb.loop = loop;
+        mb.remaining = remaining;
+        sort();
+    }
+
+    // try_update, :571-584 / can_be_inserted(hash, value), :315-326
+    bool offer_solution(worker& w, const uint64_t* x, double value, int64_t loop)
+    {
+        const uint64_t h = hash_of(x, words);
+        for (const member& mb : data)
+            if (mb.remaining == 0 && mb.value == value && mb.hash == h)
+                return false;
+        replace(w, x, value, h, loop, 0);
+        return true;
+    }
+
+    // try_advance, :556-569 / can_be_inserted(hash, constraints), :302-313
+    bool offer_advance(worker& w, const uint64_t* x, int remaining, int64_t loop)
+    {
+        const uint64_t h = hash_of(x, words);
+        for (const member& mb : data)
+            if (mb.remaining == remaining && mb.hash == h)
+                return false;
+        replace(w, x, objective(x), h, loop, remaining);
+        return true;
+    }
+};
+
+namespace {
+
+// init_with_pre_solve with both vectors present (itm-common.hpp:284-374), as
+// storage's constructor calls it.
+void
+host_pre_solve_pair(const bxg_problem& pb, engine_t& rng, double init_random,
+                    std::vector<uint64_t>& xp, std::vector<uint64_t>& xo)
+{
+    struct rc
+    {
+        float value;
+        int factor;
+        int id;
+    };
+    std::vector<rc> R(pb.max_row);
+    std::bernoulli_distribution take(init_random);
+    const bool maximize = pb.maximize != 0;
+    auto put = [](std::vector<uint64_t>& x, int i, bool v) {
+        const uint64_t bit = uint64_t{ 1 } << (i & 63);
+        if (v)
+            x[i >> 6] |= bit;
+        else
+            x[i >> 6] &= ~bit;
+    };
+
+    for (int k = 0; k != pb.m; ++k) {
+        if (!take(rng))
+            continue;
+        const int r_size = pb.row_ptr[k + 1] - pb.row_ptr[k];
+        R.resize(r_size);
+        for (int i = 0; i != r_size; ++i) {
+            const int e = pb.row_ptr[k] + i;
+            R[i] = { static_cast<float>(pb.cost[pb.row_col[e]]), pb.row_a[e], pb.row_col[e] };
+        }
+        std::shuffle(R.begin(), R.end(), rng);
+        if (maximize)
+            std::sort(R.begin(), R.end(), [](const rc& l, const rc& r) { return l.value > r.value; });
+        else
+            std::sort(R.begin(), R.end(), [](const rc& l, const rc& r) { return l.value < r.value; });
+
+        const int lo = pb.cmin[k], hi = pb.cmax[k];
+        int sum = 0, best = -2;
+        for (int i = -1; i < r_size; ++i) { // pessimistic: the shortest prefix that fits
+            if (lo <= sum && sum <= hi) {
+                best = i;
+                break;
+            }
+            if (i + 1 < r_size)
+                sum += R[i + 1].factor;
+        }
+        for (int i = 0; i != r_size; ++i)
+            put(xp, R[i].id, i <= best);
+
+        sum = 0;
+        best = -2;
+        for (int i = -1; i < r_size; ++i) { // optimistic: the longest one before the sign change
+            if (lo <= sum && sum <= hi)
+                best = i;
+            if (best != -2 && i + 1 < r_size && (maximize ? R[i + 1].value < 0 : R[i + 1].value > 0))
+                break;
+            if (i + 1 < r_size)
+                sum += R[i + 1].factor;
+        }
+        for (int i = 0; i != r_size; ++i)
+            put(xo, R[i].id, i <= best);
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int
+bxg_population_create(bxg_problem* pb, const bxg_params* p, uint64_t master_seed, int workers,
+                      bxg_population** out)
+{
+    if (!pb || !p || !out || workers < 1 || p->init_population_size < 1)
+        return fail(BXG_E_INVALID, "bxg_population_create: bad argument");
+    CUDA_TRY(cudaSetDevice(pb->device));
+    std::unique_ptr<bxg_population> q(new (std::nothrow) bxg_population);
+    if (!q)
+        return fail(BXG_E_MEMORY, "out of host memory");
+    q->pb = pb;
+    q->p = *p;
+    q->size = p->init_population_size;
+    q->words = pb->n / 64 + 1;
+    q->master.seed(static_cast<engine_t::result_type>(master_seed));
+    q->workers.resize(workers);
+    q->order.resize(q->size);
+    q->data.resize(q->size);
+    q->bastert.assign(q->words, 0);
+    q->scratch.assign(q->words, 0);
+    for (auto& mb : q->data)
+        mb.x.assign(q->words, 0);
+    CUDA_TRY(q->d_cmin.upload(pb->cmin));
+    CUDA_TRY(q->d_cmax.upload(pb->cmax));
+
+    // storage's constructor, itm-optimizer-common.hpp:162-226
+    const int n = pb->n;
+    for (int i = 0; i != n; ++i) {
+        const double c = pb->cost[i];
+        if (pb->maximize ? c > 0 : c < 0) // init_with_bastert, value_if_0 = 0
+            q->bastert[i >> 6] |= uint64_t{ 1 } << (i & 63);
+    }
+    engine_t& rng = q->master;
+    const int half = q->size / 2;
+    for (int i = 0; i != half; ++i) {
+        q->data[i].x = q->bastert;
+        std::bernoulli_distribution flip(std::clamp(static_cast<double>(i) / (5 * half), 0.0, 1.0));
+        for (int v = 0; v != n; ++v)
+            if (flip(rng))
+                q->data[i].x[v >> 6] ^= uint64_t{ 1 } << (v & 63);
+    }
+    for (int i = half; i + 1 < q->size; i += 2) {
+        for (int side = 0; side != 2; ++side) {
+            std::bernoulli_distribution one(side == 0 ? 0.2 : 0.8);
+            std::vector<uint64_t>& x = q->data[i + side].x;
+            for (int v = 0; v != n; ++v) {
+                const uint64_t bit = uint64_t{ 1 } << (v & 63);
+                if (one(rng))
+                    x[v >> 6] |= bit;
+                else
+                    x[v >> 6] &= ~bit;
+            }
+        }
+        host_pre_solve_pair(*pb, rng, std::clamp(static_cast<double>(i) / (5 * q->size), 0.0, 1.0),
+                            q->data[i].x, q->data[i + 1].x);
+    }
+
+    // score every member on the device
+    std::vector<uint64_t> flat(static_cast<size_t>(q->size) * q->words);
+    for (int i = 0; i != q->size; ++i)
+        std::copy(q->data[i].x.begin(), q->data[i].x.end(), flat.begin() + static_cast<size_t>(i) * q->words);
+    std::vector<int> rem(q->size);
+    std::vector<double> val(q->size);
+    const int rc = q->score(flat.data(), q->size, rem.data(), val.data());
+    if (rc != BXG_OK)
+        return rc;
+    for (int i = 0; i != q->size; ++i) {
+        q->data[i].hash = bxg_population::hash_of(q->data[i].x.data(), q->words);
+        q->data[i].value = val[i];
+        q->data[i].remaining = rem[i];
+        q->order[i] = i;
+    }
+    q->sort();
+    *out = q.release();
+    return BXG_OK;
+}
+
+void
+bxg_population_destroy(bxg_population* pop)
+{
+    delete pop;
+}
+
+int
+bxg_population_size(const bxg_population* pop)
+{
+    return pop ? pop->size : 0;
+}
+
+int
+bxg_population_master_state(bxg_population* pop, uint32_t* state)
+{
+    if (!pop || !state)
+        return fail(BXG_E_INVALID, "bxg_population_master_state: bad argument");
+    *state = engine_state(pop->master);
+    return BXG_OK;
+}
+
+int
+bxg_population_member(bxg_population* pop, int i, uint64_t* x_words, double* value, int* remaining,
+                      uint64_t* hash, int64_t* loop)
+{
+    if (!pop || i < 0 || i >= pop->size)
+        return fail(BXG_E_INVALID, "bxg_population_member: bad argument");
+    const bxg_population::member& mb = pop->data[pop->order[i]];
+    if (x_words)
+        std::copy(mb.x.begin(), mb.x.end(), x_words);
+    if (value)
+        *value = mb.value;
+    if (remaining)
+        *remaining = mb.remaining;
+    if (hash)
+        *hash = mb.hash;
+    if (loop)
+        *loop = mb.loop;
+    return BXG_OK;
+}
+
+int
+bxg_population_worker_seed(bxg_population* pop, int worker, uint64_t seed)
+{
+    if (!pop || worker < 0 || worker >= static_cast<int>(pop->workers.size()))
+        return fail(BXG_E_INVALID, "bxg_population_worker_seed: bad argument");
+    const bxg_params& p = pop->p;
+    bxg_population::worker& w = pop->workers[worker];
+    w = bxg_population::worker{};
+    w.rng.seed(static_cast<engine_t::result_type>(seed));
+    w.parent = std::normal_distribution<double>(p.init_crossover_solution_selection_mean,
+                                                p.init_crossover_solution_selection_stddev);
+    w.mutation_rate = std::normal_distribution<double>(p.init_mutation_variable_mean,
+                                                       p.init_mutation_variable_stddev);
+    w.mutation_value =
+      std::normal_distribution<double>(p.init_mutation_value_mean, p.init_mutation_value_stddev);
+    w.victim = std::uniform_int_distribution<int>(p.init_population_size / 5,
+                                                  p.init_population_size - 1);
+    w.mask = std::uniform_int_distribution<std::size_t>(0);
+    w.special_parent = std::bernoulli_distribution(p.init_crossover_bastert_insertion);
+    w.seeded = true;
+    return BXG_OK;
+}
+
+#define BXG_WORKER(pop, worker, name)                                                            \
+    if (!(pop) || (worker) < 0 || (worker) >= static_cast<int>((pop)->workers.size()) ||         \
+        !(pop)->workers[worker].seeded)                                                          \
+        return fail(BXG_E_INVALID, name ": bad population or worker (seed it first)");           \
+    bxg_population::worker& w = (pop)->workers[worker]
+
+int
+bxg_population_worker_state(bxg_population* pop, int worker, uint32_t* get_state,
+                            const uint32_t* set_state)
+{
+    BXG_WORKER(pop, worker, "bxg_population_worker_state");
+    if (set_state)
+        engine_set_state(w.rng, *set_state);
+    if (get_state)
+        *get_state = engine_state(w.rng);
+    return BXG_OK;
+}
+
+int
+bxg_population_reinit(bxg_population* pop, int worker, double kappa_min, double kappa_max,
+                      uint64_t* x_words, double* kappa)
+{
+    BXG_WORKER(pop, worker, "bxg_population_reinit");
+    if (!x_words || !kappa)
+        return fail(BXG_E_INVALID, "bxg_population_reinit: bad argument");
+    *kappa = pop->reinit(w, kappa_min, kappa_max, x_words);
+    return BXG_OK;
+}
+
+int
+bxg_population_crossover(bxg_population* pop, int worker, uint64_t* x_words)
+{
+    BXG_WORKER(pop, worker, "bxg_population_crossover");
+    pop->crossover(w, x_words);
+    return BXG_OK;
+}
+
+int
+bxg_population_mutation(bxg_population* pop, int worker, uint64_t* x_words)
+{
+    BXG_WORKER(pop, worker, "bxg_population_mutation");
+    pop->mutation(w, x_words);
+    return BXG_OK;
+}
+
+int
+bxg_population_try_update(bxg_population* pop, int worker, const uint64_t* x_words, double value,
+                          int64_t loop)
+{
+    BXG_WORKER(pop, worker, "bxg_population_try_update");
+    pop->offer_solution(w, x_words, value, loop);
+    return BXG_OK;
+}
+
+int
+bxg_population_try_advance(bxg_population* pop, int worker, const uint64_t* x_words, int remaining,
+                           int64_t loop)
+{
+    BXG_WORKER(pop, worker, "bxg_population_try_advance");
+    pop->offer_advance(w, x_words, remaining, loop);
+    return BXG_OK;
+}
+
+int
+bxg_population_score(bxg_population* pop, const uint64_t* x_words, int count, int32_t* remaining,
+                     double* value)
+{
+    if (!pop || !x_words || !remaining || !value || count < 0)
+        return fail(BXG_E_INVALID, "bxg_population_score: bad argument");
+    return pop->score(x_words, count, remaining, value);
+}
+
+int
+bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* status,
+                   double* value, int32_t* remaining)
+{
+    if (!b || !pop || pop->pb != b->pb)
+        return fail(BXG_E_INVALID, "bxg_optimize_round: batch and population of different problems");
+    const int L = b->n_lanes;
+    if (static_cast<int>(pop->workers.size()) < L)
+        return fail(BXG_E_INVALID, "bxg_optimize_round: fewer workers than lanes");
+    for (int l = 0; l != L; ++l)
+        if (!pop->workers[l].seeded)
+            return fail(BXG_E_INVALID, "bxg_optimize_round: seed every worker first");
+    bxg_problem* pb = b->pb;
+    CUDA_TRY(cudaSetDevice(pb->device));
+    const int xw32 = pb->dev.xw32;
+    const size_t xn = static_cast<size_t>(L) * xw32;
+
+    // reinit: x of the previous call (zeros at first) -> crossover / mutation
+    std::vector<uint32_t> x0(xn, 0u), rng0(L);
+    std::vector<double> kappa(L);
+    if (!first_round)
+        CUDA_TRY(cudaMemcpy(x0.data(), b->d_x.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
+    for (int l = 0; l != L; ++l) {
+        bxg_population::worker& w = pop->workers[l];
+        kappa[l] = pop->reinit(w, b->p.kappa_min, b->p.kappa_max,
+                               reinterpret_cast<uint64_t*>(x0.data() + static_cast<size_t>(l) * xw32));
+        rng0[l] = engine_state(w.rng);
+    }
+    if (b->d_x0.n < xn) {
+        if (b->d_x0.p)
+            cudaFree(b->d_x0.p);
+        b->d_x0.p = nullptr;
+        CUDA_TRY(b->d_x0.alloc(xn));
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_x0.p, x0.data(), sizeof(uint32_t) * xn, cudaMemcpyHostToDevice,
+                             b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_rng0.p, rng0.data(), sizeof(uint32_t) * L, cudaMemcpyHostToDevice,
+                             b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_kappa.p, kappa.data(), sizeof(double) * L, cudaMemcpyHostToDevice,
+                             b->stream));
+    // compute.init(slv, x); the Solver (P, pi) is only fresh in the first call
+    int rc = run_begin(b, nullptr, b->d_x0.p, b->d_rng0.p, first_round ? 1 : 0);
+    if (rc != BXG_OK)
+        return rc;
+
+    refresh_params(b);
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    launch_solve(pb->dev, b->prm, b->dev, b->cfg, b->stream, 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    b->launches += 1;
+    rc = fetch_ctl(b);
+    if (rc != BXG_OK)
+        return rc;
+    CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+
+    // try_update / try_advance in lane order, each on its worker's stream
+    std::vector<uint32_t> bestx(xn);
+    CUDA_TRY(cudaMemcpy(x0.data(), b->d_x.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(bestx.data(), b->d_bestx.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
+    for (int l = 0; l != L; ++l) {
+        const LaneCtl& c = b->h_ctl[l];
+        bxg_population::worker& w = pop->workers[l];
+        engine_set_state(w.rng, c.rng);
+        const size_t off = static_cast<size_t>(l) * xw32;
+        if (c.best_remaining == 0)
+            pop->offer_solution(w, reinterpret_cast<const uint64_t*>(bestx.data() + off), c.best_value,
+                                c.best_loop);
+        else
+            pop->offer_advance(w, reinterpret_cast<const uint64_t*>(x0.data() + off), c.best_remaining,
+                               b->p.limit);
+        if (status)
+            status[l] = c.status;
+        if (value)
+            value[l] = c.best_has_x ? c.best_value : 0.0;
+        if (remaining)
+            remaining[l] = c.best_remaining;
+    }
+    return BXG_OK;
+}
+
+uint64_t
+bxg_bit_array_hash(int n, const uint64_t* x_words)
+{
+    return bxg_population::hash_of(x_words, n / 64 + 1);
+}
+
+} // extern "C"
+
+#endif

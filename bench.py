@@ -79,6 +79,21 @@ def bench_params(args, mod):
     return mod.clamp_params(p)
 
 
+def measured_traffic(workload, lanes, limit):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_solve launch from
+    the committed `ncu --set full` capture of this same workload
+    (profiles/traffic.json, written from the .ncu-rep by profiles/ncu_summary.sh);
+    None when the capture was taken on another configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            d = json.load(f)
+        if (d.get("workload"), d.get("lanes"), d.get("limit")) == (workload, lanes, limit):
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -217,7 +232,9 @@ def run_reference(args):
         return 0
     inst, wname = make_instance(args.workload)
     cores = os.cpu_count() or 1
-    n_lanes = args.cpu_lanes or 2 * cores
+    # a bounded sample of the workload per step: a quarter of the restarts
+    # (about 3 s on 16 cores), so that K steps end within a minute or two
+    n_lanes = args.cpu_lanes or max(2 * cores, args.lanes // 4)
     for _ in range(args.warmup):
         cpu_solve_sample(inst, args, min(n_lanes, cores), 1)
     upd = 0
@@ -329,13 +346,19 @@ def run_engine(args):
     t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
     w = torch.tensor([float(cnt["updates"]), float(cnt["sweeps"]), cnt["algorithmic_bytes"],
                       float(launches)], dtype=torch.float64, device="cuda")
-    # incumbent exchange: best objective over ranks
-    key = torch.tensor([float(best_rem), best_value if best_rem == 0 else float("inf")],
-                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    # incumbent exchange: who holds the best solution over the
+    # ranks (all_reduce MIN over NCCL), and its bits (broadcast from the winner)
+    from baryonyx_b200 import exchange
+
+    xbits = bt.best(lane).astype(np.uint8)
+    xw = np.zeros(inst["n"] // 64 + 1, np.uint64)
+    packed = np.packbits(xbits, bitorder="little")
+    xw.view(np.uint8)[: len(packed)] = packed
+    winner, inc_rem, inc_value, inc_x = exchange.exchange_best(
+        best_rem, best_value, xw, maximize=bool(inst["maximize"]))
     wall_max, dev_ms_max = t.tolist()
     updates, sweeps, alg_bytes, launches_all = w.tolist()
 
@@ -393,10 +416,12 @@ def run_engine(args):
                        "nnz": nnz, "l2": "inputs larger than L2 (P is %.0f MB per GPU)" % (L * nnz * 8 / 1e6),
                        "device_bytes": info["device_bytes"]},
             "sweeps_per_s": sweeps / wall_max,
-            "best": {"remaining": key[0].item(), "value": key[1].item()},
+            "best": {"remaining": inc_rem, "value": inc_value if inc_rem == 0 else None, "rank": winner,
+                     "ones": int(np.unpackbits(inc_x.view(np.uint8)).sum())},
             "roofline": {"bound": "hbm", "kernel": "k_solve", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                         "traffic": None, "bytes_per_launch": per_launch_bytes,
+                         "traffic": measured_traffic(args.workload, L, args.limit),
+                         "bytes_per_launch": per_launch_bytes,
                          "ms_per_launch": 1e3 * per_launch_s},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
@@ -405,7 +430,8 @@ def run_engine(args):
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = args.cpu_lanes or 2 * cores
+            # the whole batch once on the host cores: 10-30 s of CPU work
+            n_cpu = args.cpu_lanes or min(L, 1024)
             u, _, dt, kind, threads = cpu_solve_sample(inst, args, n_cpu, 1)
             line["cpu_baseline"] = {
                 "value": u / dt, "unit": UNIT, "cores": threads, "kind": kind,

@@ -222,6 +222,70 @@ int bxg_batch_words32(const bxg_batch* b);
 int bxg_batch_begin_device(bxg_batch* b, const uint32_t* d_x0,
                            const uint32_t* d_rng, int reset_solver);
 
+/* ---- optimizer population --------------------------------------------------
+ * Replaces best_solution_recorder / storage / local_context
+ * (lib/src/itm-optimizer-common.hpp:52-594): `init_population_size` candidate
+ * vectors ordered by (remaining constraints, objective) and, per worker, the
+ * engine and distributions that pick parents, mutation rates and the member
+ * to replace.  The lanes of a batch are the workers.  The streams of the
+ * reference's std::default_random_engine and distributions are reproduced, so
+ * every operation returns what the reference returns for the same seeds.
+ * Vectors are bit_array blocks: n/64+1 64-bit words (bit-array.hpp:60-66). */
+typedef struct bxg_population bxg_population;
+
+/* best_solution_recorder's constructor (:467-480) on random_engine(master_seed):
+ * the initial members (storage's constructor, :162-226), scored on the device. */
+int bxg_population_create(bxg_problem* pb, const bxg_params* p,
+                          uint64_t master_seed, int workers,
+                          bxg_population** out);
+void bxg_population_destroy(bxg_population* pop);
+int bxg_population_size(const bxg_population* pop);
+/* state of the master engine (after the constructor) */
+int bxg_population_master_state(bxg_population* pop, uint32_t* state);
+/* storage::get_best(i), :347-350: member at sorted position i */
+int bxg_population_member(bxg_population* pop, int i, uint64_t* x_words,
+                          double* value, int* remaining, uint64_t* hash,
+                          int64_t* loop);
+/* local_context(ctx, worker, seed), :67-91 */
+int bxg_population_worker_seed(bxg_population* pop, int worker, uint64_t seed);
+/* read and / or replace the state of a worker's engine (either may be NULL) */
+int bxg_population_worker_state(bxg_population* pop, int worker,
+                                uint32_t* get_state, const uint32_t* set_state);
+/* best_solution_recorder::reinit, :528-554: x in / out, returns the kappa the
+ * restart begins with */
+int bxg_population_reinit(bxg_population* pop, int worker, double kappa_min,
+                          double kappa_max, uint64_t* x_words, double* kappa);
+/* storage::crossover(ctx, x), :373-421 */
+int bxg_population_crossover(bxg_population* pop, int worker, uint64_t* x_words);
+/* best_solution_recorder::mutation, :494-526 */
+int bxg_population_mutation(bxg_population* pop, int worker, uint64_t* x_words);
+/* best_solution_recorder::try_update, :571-584 */
+int bxg_population_try_update(bxg_population* pop, int worker,
+                              const uint64_t* x_words, double value,
+                              int64_t loop);
+/* best_solution_recorder::try_advance, :556-569 */
+int bxg_population_try_advance(bxg_population* pop, int worker,
+                               const uint64_t* x_words, int remaining,
+                               int64_t loop);
+/* remaining constraints (raw merged bounds) and default_cost_type::results of
+ * `count` vectors, on the device */
+int bxg_population_score(bxg_population* pop, const uint64_t* x_words, int count,
+                         int32_t* remaining, double* value);
+/* One call of optimize_functor::operator()'s loop body (:658-750) for every
+ * lane, the lanes being the workers: reinit (crossover / mutation of the
+ * lane's x, kappa to start from) -> compute_order::init -> sweeps with the
+ * kappa schedule -> push phase on the device -> try_update of the best
+ * solution of the call or try_advance of the final x, in lane order.  The
+ * Solver state (P, pi) persists between rounds; first_round = 1 starts from
+ * x = 0, P = pi = 0.  Per call, a lane offers its best solution once (the
+ * reference offers every solution it meets, each possibly drawing from the
+ * worker's engine in the middle of the run).  Host outputs of n_lanes
+ * entries, any may be NULL. */
+int bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round,
+                       int32_t* status, double* value, int32_t* remaining);
+/* bit_array_hash, bit-array.hpp:410-423 */
+uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
+
 #ifdef __cplusplus
 }
 #endif

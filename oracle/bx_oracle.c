@@ -2417,22 +2417,18 @@ store_if_better_value(ox_run* r, ox_best* b, double current, int64_t i)
     }
 }
 
-int
-ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
-         double* value, int* remaining_out, int64_t* loop, int64_t* updates,
-         int64_t* sweeps)
+/* The loop of solver_functor::operator() (itm-solver-common.hpp:135-225) on a
+ * run that is ready to sweep.  optimizer = 1 gives one call of a worker of
+ * optimize_functor::operator() instead (itm-optimizer-common.hpp:658-750): it
+ * starts at kappa_start (what reinit returned), the push sweep runs at kappa =
+ * pushing_k_factor and every push restarts the schedule from kappa_start.
+ * `best` tracks the best solution of the run (the optimizer offers each one to
+ * the recorder as it goes; callers that need that do it per sweep). */
+static int
+solve_loop(ox_run* r, double kappa_start, int optimizer, ox_best* best)
 {
-    ox_run* r = ox_run_begin(pb, p, seed);
-    if (!r)
-        return OX_STATUS_INTERNAL_ERROR;
-
-    ox_best best;
-    best.x = (uint64_t*)calloc((size_t)r->x_blocks, sizeof(uint64_t));
-    best.value = pb->maximize ? -INFINITY : INFINITY; /* bad_value */
-    best.loop = 0;
-    best.remaining = INT_MAX;
-    best.has_x = 0;
-
+    const ox_problem* pb = r->pb;
+    const ox_params* p = &r->p;
     int status = OX_STATUS_UNINITIALIZED;
     int best_remaining = INT_MAX;
 
@@ -2446,20 +2442,20 @@ ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
     const long w_limit = (long)p->w;
 
     int start_push = 0;
-    double kappa = p->kappa_min;
+    double kappa = kappa_start;
 
     for (int64_t i = 0; i != p->limit; ++i) {
         int remaining = order_run(r, kappa, delta, theta, 0, 0.0);
 
         if (remaining == 0) {
-            store_if_better_value(r, &best, results(r), i);
+            store_if_better_value(r, best, results(r), i);
             best_remaining = remaining;
             start_push = 1;
             break;
         }
 
         if (remaining < best_remaining) {
-            store_if_better_remaining(r, &best, remaining, i);
+            store_if_better_remaining(r, best, remaining, i);
             best_remaining = remaining;
         }
 
@@ -2476,20 +2472,23 @@ ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
         status = OX_STATUS_LIMIT_REACHED;
     } else {
         for (int push = 0; push < p->pushes_limit; ++push) {
-            int remaining = order_run(r, pushing_k_factor * kappa, delta, theta,
-                                      1, pushing_objective_amplifier);
+            int remaining =
+              order_run(r, optimizer ? pushing_k_factor : pushing_k_factor * kappa,
+                        delta, theta, 1, pushing_objective_amplifier);
 
             if (remaining == 0)
                 store_if_better_value(
-                  r, &best, results(r),
+                  r, best, results(r),
                   -(int64_t)push * p->pushing_iteration_limit - 1);
 
+            if (optimizer)
+                kappa = kappa_start;
             for (int iter = 0; iter < p->pushing_iteration_limit; ++iter) {
                 remaining = order_run(r, kappa, delta, theta, 0, 0.0);
 
                 if (remaining == 0) {
                     store_if_better_value(
-                      r, &best, results(r),
+                      r, best, results(r),
                       -(int64_t)push * p->pushing_iteration_limit - iter - 1);
                     break;
                 }
@@ -2504,8 +2503,28 @@ ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
         }
     }
 
-    if (best.remaining == 0)
+    if (best->remaining == 0)
         status = OX_STATUS_SUCCESS;
+    return status;
+}
+
+int
+ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
+         double* value, int* remaining_out, int64_t* loop, int64_t* updates,
+         int64_t* sweeps)
+{
+    ox_run* r = ox_run_begin(pb, p, seed);
+    if (!r)
+        return OX_STATUS_INTERNAL_ERROR;
+
+    ox_best best;
+    best.x = (uint64_t*)calloc((size_t)r->x_blocks, sizeof(uint64_t));
+    best.value = pb->maximize ? -INFINITY : INFINITY; /* bad_value */
+    best.loop = 0;
+    best.remaining = INT_MAX;
+    best.has_x = 0;
+
+    const int status = solve_loop(r, p->kappa_min, 0, &best);
 
     if (x) {
         for (int i = 0; i != pb->n; ++i)
@@ -2524,6 +2543,34 @@ ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
 
     free(best.x);
     ox_run_end(r);
+    return status;
+}
+
+/* solve_loop on an existing run (after ox_run_set_rng / ox_run_set_x): the
+ * Solver state (P, pi) is whatever the run holds, as for a worker of the
+ * optimizer between two calls. */
+int
+ox_run_solve(ox_run* r, double kappa_start, int optimizer, uint64_t* best_x_words,
+             double* value, int* remaining_out, int64_t* loop)
+{
+    ox_best best;
+    best.x = (uint64_t*)calloc((size_t)r->x_blocks, sizeof(uint64_t));
+    best.value = r->pb->maximize ? -INFINITY : INFINITY;
+    best.loop = 0;
+    best.remaining = INT_MAX;
+    best.has_x = 0;
+
+    const int status = solve_loop(r, kappa_start, optimizer, &best);
+
+    if (best_x_words)
+        memcpy(best_x_words, best.x, sizeof(uint64_t) * (size_t)r->x_blocks);
+    if (value)
+        *value = best.has_x ? best.value : 0.0;
+    if (remaining_out)
+        *remaining_out = best.remaining;
+    if (loop)
+        *loop = best.loop;
+    free(best.x);
     return status;
 }
 
@@ -2845,6 +2892,12 @@ uint32_t
 ox_pop_ctx_rng(ox_pop_ctx* c)
 {
     return c->rng;
+}
+
+void
+ox_pop_ctx_set_rng(ox_pop_ctx* c, uint32_t state)
+{
+    c->rng = state;
 }
 
 /* storage::choose_a_solution, itm-optimizer-common.hpp:151-160 */

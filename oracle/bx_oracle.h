@@ -161,6 +161,14 @@ int ox_solve(ox_problem* pb, const ox_params* p, uint32_t seed, int8_t* x,
              double* value, int* remaining, int64_t* loop, int64_t* updates,
              int64_t* sweeps);
 
+/* The same loop on an existing run (after ox_run_set_rng / ox_run_set_x), P and
+ * pi as the run holds them.  optimizer = 1: one call of a worker of
+ * optimize_functor::operator() (itm-optimizer-common.hpp:658-750) starting at
+ * kappa_start.  best_x_words: n/64+1 blocks. */
+int ox_run_solve(ox_run* run, double kappa_start, int optimizer,
+                 uint64_t* best_x_words, double* value, int* remaining,
+                 int64_t* loop);
+
 /* ---- Z sub-solvers (known-answer tests lib/test/lib.cpp:376-563) -------- */
 int ox_bb_solve(int maximize, double* value, int* factor, int* id, int n,
                 int bmin, int bmax);
@@ -182,6 +190,7 @@ void ox_pop_member(ox_pop* pop, int i, uint64_t* x_words, double* value,
 ox_pop_ctx* ox_pop_ctx_create(ox_pop* pop, unsigned thread_id, uint64_t seed);
 void ox_pop_ctx_destroy(ox_pop_ctx* c);
 uint32_t ox_pop_ctx_rng(ox_pop_ctx* c);
+void ox_pop_ctx_set_rng(ox_pop_ctx* c, uint32_t state);
 double ox_pop_reinit(ox_pop* pop, ox_pop_ctx* c, double kappa_min,
                      double kappa_max, uint64_t* x_words);
 void ox_pop_mutation(ox_pop* pop, ox_pop_ctx* c, uint64_t* x_words);

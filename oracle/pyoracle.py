@@ -158,6 +158,8 @@ def oracle():
     lib.ox_run_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.ox_run_set_x.argtypes = [C.c_void_p, _u64p]
     lib.ox_run_set_rng.argtypes = [C.c_void_p, C.c_uint32]
+    lib.ox_run_solve.argtypes = [C.c_void_p, C.c_double, C.c_int, _u64p, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     lib.ox_run_objective.argtypes = [C.c_void_p]
     lib.ox_run_objective.restype = C.c_double
     lib.ox_run_updates.argtypes = [C.c_void_p]
@@ -273,6 +275,14 @@ class OracleRun(_RunBase):
 
     def objective(self):
         return self.lib.ox_run_objective(self.h)
+
+    def solve(self, kappa_start: float, optimizer: bool = False):
+        """The solver_functor loop (or one optimizer call) on this run as it stands."""
+        bx = np.zeros(self.n // 64 + 1, np.uint64)
+        v, r, l = C.c_double(), C.c_int(), C.c_int64()
+        st = self.lib.ox_run_solve(self.h, kappa_start, int(optimizer), bx, C.byref(v), C.byref(r),
+                                   C.byref(l))
+        return {"status": st, "best_x": bx, "value": v.value, "remaining": r.value, "loop": l.value}
 
     def updates(self):
         return self.lib.ox_run_updates(self.h)
@@ -519,6 +529,12 @@ class Population:
 
     def ctx_rng(self, thread_id: int) -> int:
         return self._f("ctx_rng")(self.ctxs[thread_id])
+
+    def set_ctx_rng(self, thread_id: int, state: int):
+        """(oracle only) the worker's engine continues from `state`."""
+        f = self.lib.ox_pop_ctx_set_rng
+        f.argtypes = [C.c_void_p, C.c_uint32]
+        f(self.ctxs[thread_id], state)
 
     def reinit(self, thread_id: int, kappa_min: float, kappa_max: float, x: np.ndarray) -> float:
         return self._f("reinit")(self.h, self.ctxs[thread_id], kappa_min, kappa_max, x)
