@@ -160,9 +160,11 @@ def telebus(m=1500, n=7000, seed=4, linear_hi=25, name="telebus-shaped"):
                 f[0] = 2
         else:
             f = np.where(rng.rand(size) < 0.15, -1, 1)
+        kind = rng.randint(3)
+        if kind == 1 and not np.any(f > 0):
+            f[0] = -f[0]  # a ">= 1" row needs a positive coefficient to be realisable
         lower = int(f[f < 0].sum())
         upper = int(f[f > 0].sum())
-        kind = rng.randint(3)
         # pick bounds that the all-zero or a small subset can satisfy
         if kind == 0:  # <=
             cmin.append(INT_MIN)

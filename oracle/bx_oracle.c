@@ -1408,6 +1408,18 @@ ox_problem_create(int m, int n, const int* row_ptr, const int* col,
         }
     }
 
+    /* bx_ensures(b[i].min <= b[i].max), itm-solver-inequalities-Z.cpp:182 and
+     * the like: the reference terminates on an unrealisable row */
+    for (int k = 0; k != m; ++k) {
+        if (pb->bmin[k] > pb->bmax[k]) {
+            fprintf(stderr, "oracle: constraint %d is unrealisable (%d > %d)\n", k,
+                    pb->bmin[k], pb->bmax[k]);
+            pb->n_obj = 0;
+            ox_problem_destroy(pb);
+            return NULL;
+        }
+    }
+
     pb->n_obj = n_obj;
     pb->obj_var = (int*)malloc(sizeof(int) * (size_t)(n_obj + 1));
     pb->obj_factor = (double*)malloc(sizeof(double) * (size_t)(n_obj + 1));

@@ -224,6 +224,8 @@ class OracleProblem:
             len(inst["obj_var"]), i32(inst["obj_var"]),
             np.ascontiguousarray(inst["obj_factor"], np.float64), float(inst["cost_constant"]),
         )
+        if not self.h:
+            raise RuntimeError("ox_problem_create failed (unrealisable constraint?)")
         self.m, self.n, self.nnz = inst["m"], inst["n"], int(inst["row_ptr"][-1])
 
     def set_tail_value(self, v: float):
