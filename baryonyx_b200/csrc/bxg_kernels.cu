@@ -45,9 +45,6 @@ constexpr int kFam = BXG_FAM;
 #ifndef BXG_GATHER_UNROLL
 #define BXG_GATHER_UNROLL 4
 #endif
-#ifndef BXG_GROUP_BATCH
-#define BXG_GROUP_BATCH 4
-#endif
 
 // The CTA's dynamic shared memory: [Lane][Shared][row scratch][R values][pi]
 // [activities][x].  Views built from this symbol keep their address space, so
@@ -91,7 +88,6 @@ struct Lane
     const double* cost;
     double theta, delta;
     int maximize, tail_rows;
-    int group_shift; // log2 of the lanes per column in the warp-group gather (0: entry gather)
     double* P;
     double* pi;
     uint32_t* x;
@@ -588,14 +584,30 @@ affect_element(Lane& L, int r0, int id, const int4 info, double pv, bool in, dou
     if (was != set) {
         atomicXor(&x[j >> 5], bit);
         const int sgn = set ? 1 : -1;
-        for (int t = info.x; t < info.y; ++t) {
-            const int rs = L.csc_rs[t];
-            if (FAM == FAM_01)
-                atomicAdd(&act[rs >> 1], sgn);
-            else if (FAM == FAM_101)
-                atomicAdd(&act[rs >> 1], (rs & 1) ? -sgn : sgn);
-            else
-                atomicAdd(&act[rs >> 1], sgn * L.csc_a[t]);
+        // the rows of the column, eight independent loads at a time (the CTA
+        // waits for the few threads whose bit flips: one memory round trip
+        // per eight entries instead of one per entry)
+        const int* __restrict__ csc_rs = L.csc_rs;
+        const int t_last = info.y - 1;
+        for (int t0 = info.x; t0 < info.y; t0 += 8) {
+            int rs[8], a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u < t_last ? t0 + u : t_last;
+                rs[u] = csc_rs[t];
+                a[u] = FAM == FAM_Z ? L.csc_a[t] : 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (t0 + u < info.y) {
+                    if (FAM == FAM_01)
+                        atomicAdd(&act[rs[u] >> 1], sgn);
+                    else if (FAM == FAM_101)
+                        atomicAdd(&act[rs[u] >> 1], (rs[u] & 1) ? -sgn : sgn);
+                    else
+                        atomicAdd(&act[rs[u] >> 1], sgn * a[u]);
+                }
+            }
         }
     }
 }
@@ -638,7 +650,7 @@ merge_min2(unsigned long long& m1, unsigned long long& m2, unsigned long long o1
 //    order with the reference's two accumulators, so the sums are bit-equal.
 // B. selection without ordering when all values differ (the usual case once
 //    pi and P have moved): two smallest keys, or the boundary by sign.
-template<int FAM, bool SM, bool GROUP>
+template<int FAM, bool SM>
 __device__ __noinline__ void
 update_row(int k, int k_next, double kappa, int push, double obj_amp)
 {
@@ -716,105 +728,6 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         pown[i] = own;
     };
 
-    if constexpr (GROUP) {
-// @region update_row.ggather
-        // Columns of at most W = 8, 16 or 32 entries: a group of W adjacent
-        // lanes reads one column's run of P (contiguous in CSC order) and the
-        // rows of its entries, so a load instruction of the warp touches 32 / W
-        // runs, each coalesced, and the address comes straight from row_info:
-        // two dependent memory round trips (row_info, then P and rows) instead
-        // of the entry path's gp -> P chain per trip plus the stage-2 loads,
-        // no staging through shared memory and no barrier inside the gather.
-        // The terms of a column are then added left to right with the
-        // reference's two accumulators, each lane of the group fetching them
-        // by shuffle; lanes past the column's end contribute +0.0, which never
-        // changes a sum that started from +0.0.
-        constexpr int GB = BXG_GROUP_BATCH; // iterations whose loads are in flight together
-        const int wshift = L.group_shift;
-        const int W = 1 << wshift;
-        const int t = ln & (W - 1);          // my offset inside the column
-        const int gbase = ln & ~(W - 1);     // first lane of my group
-        const int grp = ln >> wshift;        // which of the 32 / W columns of an iteration
-        const int epi_shift = 5 - wshift;    // log2(columns per iteration)
-        const int* __restrict__ csc_rs = L.csc_rs;
-        // warp w owns the elements [w * q, (w + 1) * q) of the row, 32 per trip
-        const int q = (r_size + nw - 1) / nw;
-        const int e_first = wp * q;
-        const int e_end = e_first + q < r_size ? e_first + q : r_size;
-        int4 info_next = make_int4(0, 0, 0, 0);
-        if (e_first + ln < e_end)
-            info_next = row_info[r0 + e_first + ln];
-        for (int base = e_first; base < e_end; base += 32) {
-            const int e_own = base + ln;
-            const int4 info = info_next; // c0, c1, own CSC position, column
-            if (e_own + 32 < e_end)
-                info_next = row_info[r0 + e_own + 32];
-            else
-                info_next = make_int4(0, 0, 0, 0);
-            const double cj = e_own < e_end ? cost[info.w] : 0.0;
-            const int n_el = e_end - base < 32 ? e_end - base : 32;
-            const int maxlen = __reduce_max_sync(0xffffffffu, info.y - info.x);
-            // iterations that still hold an element of this trip
-            const int n_it = (n_el + (1 << epi_shift) - 1) >> epi_shift;
-            for (int it0 = 0; it0 < n_it; it0 += GB) {
-                double p[GB];
-                int rs[GB];
-#pragma unroll
-                for (int u = 0; u < GB; ++u) {
-                    const int el = ((it0 + u) << epi_shift) + grp; // element of the trip my group serves
-                    const int c0 = __shfl_sync(0xffffffffu, info.x, el & 31);
-                    const int c1 = __shfl_sync(0xffffffffu, info.y, el & 31);
-                    const bool on = it0 + u < n_it && c0 + t < c1;
-                    p[u] = 0.0;
-                    rs[u] = -1;
-                    if (on) {
-                        p[u] = gP[c0 + t];
-                        rs[u] = csc_rs[c0 + t];
-                    }
-                }
-                if (base == e_first && it0 == 0 && tid < nh.y)
-                    ni = row_info[nh.x + tid]; // prefetch, first half (see below)
-#pragma unroll
-                for (int u = 0; u < GB; ++u) {
-                    if (it0 + u < n_it) {
-                        const int el = ((it0 + u) << epi_shift) + grp;
-                        double pv = 0.0, a_pi = 0.0;
-                        bool mine = false;
-                        if (rs[u] >= 0) {
-                            a_pi = s_pi[rs[u] >> 1];
-                            pv = p[u];
-                            mine = (rs[u] >> 1) == k;
-                            if (mine)
-                                pv = __dmul_rn(pv, theta);
-                            if (FAM != FAM_01 && (rs[u] & 1)) {
-                                pv = -pv;
-                                a_pi = -a_pi;
-                            }
-                        }
-                        double sum_pi = 0.0, sum_p = 0.0;
-                        for (int tt = 0; tt < maxlen; ++tt) {
-                            sum_pi = __dadd_rn(sum_pi, __shfl_sync(0xffffffffu, a_pi, gbase + tt));
-                            sum_p = __dadd_rn(sum_p, __shfl_sync(0xffffffffu, pv, gbase + tt));
-                        }
-                        const unsigned bm = __ballot_sync(0xffffffffu, mine) >> gbase;
-                        const unsigned gm = W == 32 ? bm : (bm & ((1u << W) - 1u));
-                        const double own = __shfl_sync(0xffffffffu, pv, gbase + (gm ? __ffs(gm) - 1 : 0));
-                        const double cje = __shfl_sync(0xffffffffu, cj, el & 31);
-                        if (t == 0 && el < n_el) {
-                            const double v = __dsub_rn(__dsub_rn(cje, sum_pi), sum_p);
-                            key0[base + el] = (unsigned long long)__double_as_longlong(v);
-                            pown[base + el] = own;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (e_own < e_end)
-                finish(e_own, cj, __longlong_as_double((long long)key0[e_own]), pown[e_own]);
-        }
-        if (tid == 0)
-            t_gather = clock64();
-    } else {
 // @region update_row.chunk
     for (int ia = 0; ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
@@ -823,15 +736,18 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         int fb = S;
         if (S - fa > stage_cap) {
             int lo = ia + 1, hi = r_size; // last ib with eptr[ib] - fa <= cap
+            // (row_eptr has one entry per element: the end of the last
+            // element is S, not the entry after it)
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (row_eptr[r0 + mid] - fa <= stage_cap)
+                const int end = mid < r_size ? row_eptr[r0 + mid] : S;
+                if (end - fa <= stage_cap)
                     lo = mid;
                 else
                     hi = mid - 1;
             }
             ib = lo;
-            fb = row_eptr[r0 + ib];
+            fb = ib < r_size ? row_eptr[r0 + ib] : S;
         }
 
 // @region update_row.stage1
@@ -892,7 +808,6 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         ia = ib;
         if (ia < r_size)
             __syncthreads(); // the staging buffer is reused
-    }
     }
 
 // @region update_row.prefetch2
@@ -1548,19 +1463,10 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
         else
             update_row_z<false>(k, kappa, push, obj_amp);
 #else
-        // (the gather is a template parameter so that each variant only
-        // carries its own registers)
-        if (L.all_smem) {
-            if (L.group_shift)
-                update_row<kFam, true, true>(k, k_next, kappa, push, obj_amp);
-            else
-                update_row<kFam, true, false>(k, k_next, kappa, push, obj_amp);
-        } else {
-            if (L.group_shift)
-                update_row<kFam, false, true>(k, k_next, kappa, push, obj_amp);
-            else
-                update_row<kFam, false, false>(k, k_next, kappa, push, obj_amp);
-        }
+        if (L.all_smem)
+            update_row<kFam, true>(k, k_next, kappa, push, obj_amp);
+        else
+            update_row<kFam, false>(k, k_next, kappa, push, obj_amp);
 #endif
     }
 
@@ -1628,7 +1534,6 @@ struct SmemPlan
     int pi_in_smem, x_in_smem, r_in_smem;
     int sort_cap;
     int stage_cap;
-    int group_shift;
 };
 
 // Bytes of the per-lane row scratch (key0, sk, pown, sid), laid out the
@@ -1718,7 +1623,6 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.delta = pr.delta;
         L.maximize = pb.maximize;
         L.tail_rows = pb.tail_rows;
-        L.group_shift = plan.group_shift;
         L.sh = sh;
         L.P = b.P + (size_t)lane_id * pb.nnz;
         L.ctl = ctl;
@@ -2175,37 +2079,15 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     cfg.sort_cap = pow2_at_least(pb.max_row);
     // staging buffer of the reduced-cost gather: at least one column, at most
     // the longest row's entries
-    // Columns of at most 32 entries (01 / 101 families): the warp-group gather,
-    // W = 8, 16 or 32 lanes per column and no staging buffer.  BXG_GATHER=entry
-    // keeps the entry gather (experiments, parity tests of both).
-    cfg.group_shift = 0;
-    if (pb.family != FAM_Z && pb.max_col <= 32)
-        cfg.group_shift = pb.max_col <= 8 ? 3 : pb.max_col <= 16 ? 4 : 5;
-    if (const char* env = getenv("BXG_GATHER"))
-        if (env[0] == 'e')
-            cfg.group_shift = 0;
-    const int stage_min = cfg.group_shift ? 0 : (pb.max_col > 256 ? pb.max_col : 256);
-    cfg.stage_cap = cfg.group_shift ? 0 : (pb.max_S < stage_min ? stage_min : pb.max_S);
+    const int stage_min = pb.max_col > 256 ? pb.max_col : 256;
+    const int stage_max = pb.max_S < stage_min ? stage_min : pb.max_S;
+    cfg.stage_cap = stage_min;
     auto bytes = [&]() {
         return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap,
                           cfg.stage_cap);
     };
-    {
-        // a smaller staging buffer (rows summed in chunks) when that lets
-        // seven lanes share an SM (what the registers of the 128- and
-        // 160-thread classes allow)
-        const size_t target = (size_t)per_sm / 7 - 1024;
-        if (!cfg.group_shift && bytes() > target) {
-            cfg.stage_cap = stage_min;
-            const size_t fixed = bytes();
-            if (fixed < target) {
-                cfg.stage_cap += (int)((target - fixed) / sizeof(double2));
-                if (cfg.stage_cap > pb.max_S)
-                    cfg.stage_cap = pb.max_S;
-            }
-        }
-    }
-    // drop the largest consumers first until the plan fits
+    // with the smallest staging buffer, drop the largest consumers first until
+    // the plan fits
     if (bytes() > budget)
         cfg.x_in_smem = 0;
     if (bytes() > budget) {
@@ -2216,6 +2098,21 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     }
     if (bytes() > budget)
         cfg.pi_in_smem = 0;
+    if (!cfg.r_in_smem)
+        cfg.stage_cap = stage_max; // the scratch lives in global memory
+    else {
+        // then let the staging buffer grow (rows are summed in chunks when it
+        // is shorter than the row's expansion): up to what lets seven lanes
+        // share an SM -- the registers of the 128-thread class allow as many --
+        // or, when the rest alone is past that, up to the CTA's limit
+        const size_t target = (size_t)per_sm / 7 - 1024;
+        const size_t fixed = bytes();
+        const size_t limit = fixed < target ? target : budget;
+        const size_t room = fixed < limit ? limit - fixed : 0;
+        const size_t grow = room / sizeof(double2);
+        cfg.stage_cap = (size_t)stage_min + grow > (size_t)stage_max ? stage_max
+                                                                     : stage_min + (int)grow;
+    }
     cfg.smem = bytes();
 
     // One thread per row element in the second gather stage (whole warps),
@@ -2245,6 +2142,7 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     if (t > 1024)
         t = 1024;
     cfg.threads = t;
+
     return cfg;
 }
 
@@ -2298,8 +2196,7 @@ BXG_FAM_FN(launch_begin)(const DevProblem& pb, const DevParams& pr, const DevBat
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap,
-                   cfg.group_shift };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
                init_on_device, init_random, d_cost_orig, plan);
 }
@@ -2308,8 +2205,7 @@ void
 BXG_FAM_FN(launch_order_init)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap,
-                   cfg.group_shift };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
 }
 
@@ -2317,8 +2213,7 @@ void
 BXG_FAM_FN(launch_sweep)(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap,
-                   cfg.group_shift };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
 }
 
@@ -2326,8 +2221,7 @@ void
 BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s, int optimizer)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap,
-                   cfg.group_shift };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan, optimizer);
 }
 
@@ -2335,8 +2229,7 @@ void
 BXG_FAM_FN(launch_objective)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap,
-                   cfg.group_shift };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 

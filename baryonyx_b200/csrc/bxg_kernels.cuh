@@ -161,7 +161,6 @@ struct LaunchCfg
     int pi_in_smem, x_in_smem, r_in_smem;
     int sort_cap;
     int stage_cap;
-    int group_shift; // warp-group gather: log2 lanes per column (0 = entry gather)
 };
 
 LaunchCfg plan_launch(const DevProblem& pb, int device, int n_lanes);
