@@ -70,7 +70,7 @@ EXPORTS = [
     "bxg_batch_begin", "bxg_batch_get_state", "bxg_batch_set_state", "bxg_batch_sweep",
     "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
     "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_launches",
-    "bxg_batch_words32", "bxg_batch_begin_device",
+    "bxg_batch_words32", "bxg_batch_begin_device", "bxg_batch_set_lane_params",
     "bxg_population_create", "bxg_population_destroy", "bxg_population_size",
     "bxg_population_master_state", "bxg_population_member", "bxg_population_worker_seed",
     "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
@@ -290,6 +290,21 @@ class Batch:
         ph = (C.c_int64 * 4)()
         check(lib().bxg_batch_path_counters(self.h, u, c, ph))
         return {"updates": list(u), "cycles": list(c), "phase_cycles": list(ph)}
+
+    def set_lane_params(self, theta=None, delta=None, kappa_min=None, kappa_step=None,
+                        init_policy_random=None):
+        """Per-lane theta / delta / kappa_min / kappa_step / init_policy_random (parameter sweeps)."""
+        arrs = []
+        for a in (theta, delta, kappa_min, kappa_step, init_policy_random):
+            if a is None:
+                arrs.append(None)
+            else:
+                a = np.ascontiguousarray(a, np.float64)
+                assert a.shape == (self.n_lanes,)
+                arrs.append(a)
+        f = lib().bxg_batch_set_lane_params
+        f.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        check(f(self.h, *[_ptr(a) for a in arrs]))
 
     def reset_counters(self):
         check(lib().bxg_batch_reset_counters(self.h))

@@ -131,7 +131,8 @@ struct bxg_batch
     double tail_value = 0;
     std::vector<double> norm_cost, powtab;
 
-    DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_Rv;
+    DevBuf<double> d_P, d_pi, d_norm_cost, d_powtab, d_kappa, d_Rv, d_lane_par;
+    std::vector<double> lane_par; // [lanes][5] or empty (bxg_batch_set_lane_params)
     DevBuf<unsigned char> d_scratch, d_zscratch;
     DevBuf<uint32_t> d_x, d_bestx, d_seeds, d_x0, d_rng0;
     DevBuf<int> d_oR, d_act;
@@ -886,6 +887,7 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     d.mo = b->d_mo.p;
     d.ctl = b->d_ctl.p;
     d.kappa = b->d_kappa.p;
+    d.lane_par = nullptr;
     d.g_scratch = b->cfg.r_in_smem ? nullptr : b->d_scratch.p;
     d.z_scratch = zbytes ? b->d_zscratch.p : nullptr;
     d.z_bytes = zbytes;
@@ -1043,7 +1045,8 @@ run_begin(bxg_batch* b, const uint32_t* h_seeds, const uint32_t* d_x0, const uin
                 std::default_random_engine rng(h_seeds[l]);
                 std::vector<uint64_t> x(words, 0);
                 host_pre_solve(*pb, b->p.init_policy == 2, rng, x);
-                std::bernoulli_distribution choose_mutation(b->p.init_policy_random);
+                std::bernoulli_distribution choose_mutation(
+                  b->lane_par.empty() ? b->p.init_policy_random : b->lane_par[5 * size_t(l) + 4]);
                 for (int i = 0; i != pb->n; ++i)
                     if (choose_mutation(rng))
                         x[i / 64] ^= uint64_t{ 1 } << (i % 64);
@@ -1386,6 +1389,58 @@ bxg_batch_path_counters(bxg_batch* b, int64_t* updates, int64_t* cycles, int64_t
             phase_cycles[i] = ph;
         }
     }
+    return BXG_OK;
+}
+
+int
+bxg_batch_set_lane_params(bxg_batch* b, const double* theta, const double* delta,
+                          const double* kappa_min, const double* kappa_step,
+                          const double* init_policy_random)
+{
+    if (!b)
+        return fail(BXG_E_INVALID, "null batch");
+    CUDA_TRY(cudaSetDevice(b->pb->device));
+    if (!theta && !delta && !kappa_min && !kappa_step && !init_policy_random) {
+        b->lane_par.clear();
+        b->dev.lane_par = nullptr;
+        return BXG_OK;
+    }
+    const int L = b->n_lanes;
+    // the smallest non-zero normalised cost, for the automatic delta
+    double mini = std::numeric_limits<double>::max();
+    for (double c : b->norm_cost)
+        if (c)
+            mini = std::min(mini, std::abs(c));
+
+    b->lane_par.assign(5 * static_cast<size_t>(L), 0.0);
+    for (int l = 0; l != L; ++l) {
+        // every lane goes through context_set_solver_parameters' clamps
+        // (private.cpp:51-172) like a run of its own
+        bxg_params in = b->p, out;
+        if (theta)
+            in.theta = theta[l];
+        if (delta)
+            in.delta = delta[l];
+        if (kappa_min)
+            in.kappa_min = kappa_min[l];
+        if (kappa_step)
+            in.kappa_step = kappa_step[l];
+        if (init_policy_random)
+            in.init_policy_random = init_policy_random[l];
+        // w was already turned into a sweep count by the first clamp
+        const double w = in.w;
+        bxg_clamp_params(&in, &out);
+        out.w = w;
+        double* par = &b->lane_par[5 * static_cast<size_t>(l)];
+        par[0] = out.theta;
+        // compute_delta, itm-common.hpp:917-933, with the lane's theta
+        par[1] = out.delta < 0 ? mini - out.theta * mini : out.delta;
+        par[2] = out.kappa_min;
+        par[3] = out.kappa_step;
+        par[4] = out.init_policy_random;
+    }
+    CUDA_TRY(b->d_lane_par.upload(b->lane_par));
+    b->dev.lane_par = b->d_lane_par.p;
     return BXG_OK;
 }
 

@@ -86,7 +86,8 @@ struct Lane
     const int* csc_rs;
     const int* csc_a;
     const double* cost;
-    double theta, delta;
+    double theta, delta;          // of this lane (bxg_batch_set_lane_params)
+    double kappa_min, kappa_step; // idem
     int maximize, tail_rows;
     double* P;
     double* pi;
@@ -277,7 +278,7 @@ affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0
     double npi;
     bool moves;
     const double d =
-      affect_step(L.pr->delta, L.sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
+      affect_step(L.delta, L.sh->kk, old_pi, selected, r_size, v0, vsel, vnext, npi, moves);
     if (moves) {
         L.pi[k] = npi;
         if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
@@ -814,7 +815,10 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     // prefetch, second half: every 32-byte sector of the next row's columns
     // goes to L2 now; its gather starts after this row's selection and affect.
     if (k_next >= 0) {
-        for (int i = tid; i < nh.y; i += T) {
+        // (a row a few elements longer than the CTA: the tail is not worth a
+        // second trip with its own row_info round trip)
+        const int n_pref = nh.y <= T + 32 && nh.y > T ? T : nh.y;
+        for (int i = tid; i < n_pref; i += T) {
             if (i >= T)
                 ni = row_info[nh.x + i];
             const char* a = reinterpret_cast<const char*>(gP + ni.x);
@@ -1099,7 +1103,7 @@ update_row_z(int k, double kappa, int push, double obj_amp)
     const RowHdr hdr = pb.row_hdr[k];
     const int r0 = hdr.r0;
     const int r_size = hdr.r_size;
-    const double theta = pr.theta;
+    const double theta = L.theta;
     const bool maximize = pb.maximize != 0;
     const double* __restrict__ cost = pr.cost;
     double* const s_pi = view<SM>(L.pi, L.o_pi);
@@ -1228,7 +1232,7 @@ update_row_z(int k, double kappa, int push, double obj_amp)
         if ((__double_as_longlong(old_pi) < 0) != (__double_as_longlong(npi) < 0))
             sh->pi_changed = 1;
         sh->selected = selected;
-        sh->d = __dadd_rn(sh->kk, pr.delta);
+        sh->d = __dadd_rn(sh->kk, L.delta);
     }
     __syncthreads();
 
@@ -1619,8 +1623,11 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.csc_rs = pb.csc_rs;
         L.csc_a = pb.csc_a;
         L.cost = pr.cost;
-        L.theta = pr.theta;
-        L.delta = pr.delta;
+        const double* par = b.lane_par ? b.lane_par + 5 * (size_t)lane_id : nullptr;
+        L.theta = par ? par[0] : pr.theta;
+        L.delta = par ? par[1] : pr.delta;
+        L.kappa_min = par ? par[2] : pr.kappa_min;
+        L.kappa_step = par ? par[3] : pr.kappa_step;
         L.maximize = pb.maximize;
         L.tail_rows = pb.tail_rows;
         L.sh = sh;
@@ -1761,6 +1768,7 @@ k_begin(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
             g_Rv[i] = (i == pb.max_row) ? pr.tail_value : 0.0;
     }
 
+    const double lane_init_random = b.lane_par ? b.lane_par[5 * (size_t)lane_id + 4] : init_random;
     uint32_t rng;
     if (init_on_device) {
         // linear_congruential_engine::seed: 0 (mod m) becomes 1
@@ -1783,7 +1791,7 @@ k_begin(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
                     bool bit = pb.maximize ? (c > 0) : (c < 0);
                     const uint32_t g1 = lcg_next(cur);
                     const uint32_t g2 = lcg_next(cur);
-                    if (canonical_from(g1, g2) < init_random)
+                    if (canonical_from(g1, g2) < lane_init_random)
                         bit = !bit;
                     word |= (uint32_t)bit << (i - i0);
                 }
@@ -1925,7 +1933,8 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
     // restart begins at the kappa best_solution_recorder::reinit returned, the
     // push sweep runs at kappa = pushing_k_factor and every push restarts the
     // schedule from that kappa
-    const double kappa_start = optimizer ? b.kappa[lane_id] : pr.kappa_min;
+    const double kappa_start = optimizer ? b.kappa[lane_id] : L.kappa_min;
+    const double kappa_step = L.kappa_step;
     double kappa = kappa_start;
 
     for (long long i = 0; i != pr.limit; ++i) {
@@ -1947,7 +1956,7 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
         }
 
         if (i > w_limit)
-            kappa = __dadd_rn(kappa, __dmul_rn(pr.kappa_step, pr.powtab[remaining]));
+            kappa = __dadd_rn(kappa, __dmul_rn(kappa_step, pr.powtab[remaining]));
 
         if (kappa > pr.kappa_max) {
             status = 4; // kappa_max_reached
@@ -1984,7 +1993,7 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
                 }
 
                 if ((double)iter > pr.w)
-                    kappa = __dadd_rn(kappa, __dmul_rn(pr.kappa_step, pr.powtab[remaining]));
+                    kappa = __dadd_rn(kappa, __dmul_rn(kappa_step, pr.powtab[remaining]));
 
                 if (kappa > pr.kappa_max)
                     break;

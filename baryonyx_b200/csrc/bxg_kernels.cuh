@@ -147,6 +147,9 @@ struct DevBatch
     int2* mo;        // [lanes][order_cap]
     LaneCtl* ctl;    // [lanes]
     double* kappa;   // [lanes] input of bxg_batch_sweep
+    // [lanes][5] theta, delta, kappa_min, kappa_step, init_policy_random of each
+    // lane (parameter sweeps), or nullptr: the batch's values for every lane
+    const double* lane_par;
     // row scratch when it does not fit the shared-memory budget, else nullptr
     unsigned char* g_scratch; // [lanes][lane_scratch_bytes]
     // (Z) items / node stack / subvector pool of the sub-solvers

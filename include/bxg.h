@@ -210,6 +210,19 @@ int bxg_batch_reset_counters(bxg_batch* b);
  * may be NULL. */
 int bxg_batch_path_counters(bxg_batch* b, int64_t* updates, int64_t* cycles,
                             int64_t* phase_cycles);
+/* Parameter sweeps: per-lane values of the parameters the reference's
+ * auto-tuners vary from run to run (manual-optimizer.cpp:130-160: theta, delta,
+ * kappa-min, kappa-step, init-policy-random; nlopt-optimizer.cpp:101-103),
+ * so that one batch runs the whole grid at once.  Arrays of n_lanes entries;
+ * a NULL array keeps the batch's value for every lane, all NULL removes the
+ * per-lane values.  Every lane's set goes through the clamps of
+ * context_set_solver_parameters (private.cpp:51-172); delta < 0 = automatic
+ * (compute_delta with the lane's theta, itm-common.hpp:917-933).  Takes
+ * effect at the next bxg_batch_begin / bxg_batch_sweep. */
+int bxg_batch_set_lane_params(bxg_batch* b, const double* theta,
+                              const double* delta, const double* kappa_min,
+                              const double* kappa_step,
+                              const double* init_policy_random);
 /* Device time of the last bxg_batch_sweep / bxg_batch_solve, CUDA events on
  * the batch's stream, milliseconds. */
 int bxg_batch_last_ms(bxg_batch* b, float* ms);

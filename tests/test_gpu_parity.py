@@ -229,3 +229,60 @@ def test_set_state_roundtrip_and_carry_over():
         assert rem[0] == ref and rem[1] == ref
     assert util.states_equal(r.state(), bt.state(0))[0]
     r.close(), bt.close(), pb.close(), op.close()
+
+
+def test_parameter_sweep_lanes():
+    """bxg_batch_set_lane_params: every lane runs its own theta / delta /
+    kappa_min / kappa_step / init_policy_random (the grid of the reference's
+    manual auto-tuner, manual-optimizer.cpp:130-160) and matches an oracle run
+    with those parameters, sweep by sweep and as a whole solve."""
+    inst = synth.spp(m=60, n=600, lo=3, hi=6, seed=4, cost_hi=3)
+    grid = [
+        dict(theta=0.5, delta=-1.0, kappa_min=0.0, kappa_step=1e-3, init_policy_random=0.5),
+        dict(theta=0.3, delta=-1.0, kappa_min=0.05, kappa_step=2e-3, init_policy_random=0.1),
+        dict(theta=0.7, delta=0.01, kappa_min=0.1, kappa_step=5e-3, init_policy_random=0.9),
+        dict(theta=1.5, delta=-3.0, kappa_min=0.0, kappa_step=1e-2, init_policy_random=0.0),  # clamped
+        dict(theta=0.0, delta=0.0, kappa_min=0.2, kappa_step=0.0, init_policy_random=1.0),
+    ]
+    base = dict(limit=60, pushes_limit=3, pushing_iteration_limit=5)
+    seeds = [31, 32, 33, 34, 35]
+    cps = [po.clamp_params(util.params(**base, **g)) for g in grid]
+    op = po.OracleProblem(inst)
+    pb = capi.Problem(inst)
+    bt = pb.batch(len(grid), to_capi(po.clamp_params(util.params(**base))))
+    bt.set_lane_params(**{k: np.array([g[k] for g in grid]) for k in grid[0]})
+
+    # sweep by sweep with each lane's kappa schedule
+    bt.begin(seeds)
+    runs = [op.run(cp, s) for cp, s in zip(cps, seeds)]
+    kappa = np.array([cp.kappa_min for cp in cps])
+    for s in range(25):
+        rem = bt.sweep(kappa)
+        ref = [r.sweep(kappa[l]) for l, r in enumerate(runs)]
+        assert list(rem) == ref, s
+        for l, r in enumerate(runs):
+            ok, k = util.states_equal(r.state(), bt.state(l))
+            assert ok, (s, l, k)
+        if s > cps[0].w:
+            kappa = kappa + np.array([cp.kappa_step for cp in cps]) * (np.asarray(ref) / inst["m"]) ** cps[0].alpha
+    for r in runs:
+        r.close()
+
+    # whole solves
+    bt.begin(seeds)
+    out = bt.solve()
+    for l, (cp, s) in enumerate(zip(cps, seeds)):
+        o = op.solve(cp, s)
+        assert out["status"][l] == o["status"], l
+        assert out["remaining"][l] == o["remaining"], l
+        assert out["loop"][l] == o["loop"], l
+        assert out["value"][l] == o["value"], l
+        assert np.array_equal(bt.best(l), o["x"]), l
+
+    # back to the batch's values
+    bt.set_lane_params()
+    bt.begin(seeds)
+    out = bt.solve()
+    o = op.solve(po.clamp_params(util.params(**base)), seeds[3])
+    assert out["loop"][3] == o["loop"] and np.array_equal(bt.best(3), o["x"])
+    bt.close(), pb.close(), op.close()
