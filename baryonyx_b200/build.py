@@ -56,7 +56,10 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     procs = []
     for src, obj, defs in UNITS:
-        cmd = ([nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) +
+        # BXG_NVCC_FLAGS: extra flags for profiling builds, e.g. -DBXG_TIMERS=1
+        # (per-path / per-phase cycle counters, tools/exp_perf.py)
+        extra = os.environ.get("BXG_NVCC_FLAGS", "").split()
+        cmd = ([nvcc()] + NVCC_FLAGS + defs + extra + (["-Xptxas", "-v"] if verbose else []) +
                ["-c", os.path.join(CSRC, src), "-o", os.path.join(OBJDIR, obj)] + ccbin)
         log = open(os.path.join(OBJDIR, obj + ".log"), "w")
         procs.append((cmd, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT)))

@@ -45,6 +45,12 @@ constexpr int kFam = BXG_FAM;
 #ifndef BXG_GATHER_UNROLL
 #define BXG_GATHER_UNROLL 4
 #endif
+#ifndef BXG_CLASS_160
+#define BXG_CLASS_160 0
+#endif
+#ifndef BXG_TIMERS
+#define BXG_TIMERS 0 // -DBXG_TIMERS=1: per-path / per-phase cycle counters (profiling builds)
+#endif
 
 // The CTA's dynamic shared memory: [Lane][Shared][row scratch][R values][pi]
 // [activities][x].  Views built from this symbol keep their address space, so
@@ -682,8 +688,12 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
 
     if (tid == 0)
         L.alg_bytes += hdr.bytes;
+#if BXG_TIMERS
+    // cycle stamps of thread 0 (bxg_batch_path_counters); a build option: the
+    // four 64-bit stamps cost every thread eight registers
     const long long t_start = tid == 0 ? clock64() : 0;
     long long t_gather = t_start, t_sums = 0, t_ties = 0;
+#endif
     // {r0, r_size} of the row the sweep visits next: its P lines are sent
     // for while this row is being processed (see "prefetch" below)
     int2 nh = make_int2(0, 0);
@@ -788,8 +798,10 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         if (ia == 0 && tid < nh.y)
             ni = row_info[nh.x + tid];
         __syncthreads();
+#if BXG_TIMERS
         if (ia == 0 && tid == 0)
             t_gather = clock64();
+#endif
 
 // @region update_row.stage2
         // stage 2: elements, each adding its column's terms left to right
@@ -839,8 +851,10 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     const int tab_gen0 = L.tab_gen;
     const int tab_dirty0 = L.tab_dirty;
     const bool raw = __syncthreads_or(odd) != 0;
+#if BXG_TIMERS
     if (tid == 0)
         t_sums = clock64();
+#endif
     int n_pre = 0, n_zero = 0;
     if (!is_eq) {
         counts = 0;
@@ -945,7 +959,9 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         const bool any_dup = __syncthreads_or(dup) != 0;
         if (tid == 0) {
             L.tab_gen = tab_gen;
+#if BXG_TIMERS
             t_ties = clock64();
+#endif
         }
         if (any_dup)
             mode = 1; // equal values: their runs draw from the engine
@@ -994,13 +1010,15 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
             }
             __syncthreads();
             if (tid == 0) {
-                const long long t_end = clock64();
                 L.n_path[mode] += 1;
+#if BXG_TIMERS
+                const long long t_end = clock64();
                 L.cyc_path[mode] += (unsigned long long)(t_end - t_start);
                 L.cyc_phase[0] += (unsigned long long)(t_gather - t_start);
                 L.cyc_phase[1] += (unsigned long long)(t_sums - t_gather);
                 L.cyc_phase[2] += (unsigned long long)(t_ties - t_sums);
                 L.cyc_phase[3] += (unsigned long long)(t_end - t_ties);
+#endif
             }
             return;
         }
@@ -1048,7 +1066,9 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     __syncthreads();
     if (tid == 0) {
         L.n_path[slow ? 0 : 1] += 1;
+#if BXG_TIMERS
         L.cyc_path[slow ? 0 : 1] += (unsigned long long)(clock64() - t_start);
+#endif
     }
 }
 
@@ -2186,6 +2206,8 @@ set_smem(K kernel, size_t smem)
             BXG_LAUNCH_CLASS(KERNEL, 96, 8, GRID, CFG, STREAM, __VA_ARGS__);                \
         else if ((CFG).threads <= 128)                                                      \
             BXG_LAUNCH_CLASS(KERNEL, 128, 7, GRID, CFG, STREAM, __VA_ARGS__);               \
+        else if ((CFG).threads <= 160 && BXG_CLASS_160)                                     \
+            BXG_LAUNCH_CLASS(KERNEL, 160, 7, GRID, CFG, STREAM, __VA_ARGS__);               \
         else if ((CFG).threads <= 192)                                                      \
             BXG_LAUNCH_CLASS(KERNEL, 192, 5, GRID, CFG, STREAM, __VA_ARGS__);               \
         else if ((CFG).threads <= 256)                                                      \

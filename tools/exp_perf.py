@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Experiment driver (GPU box): one bench step of the SPP workload with the
 launch knobs taken from the environment; prints time and the per-path
-counters.  usage: python tools/exp_perf.py [--lanes N] [--limit K] [--workload W]"""
+counters.  usage: python tools/exp_perf.py [--lanes N] [--limit K] [--workload W]
+The cycle counters need a profiling build: BXG_NVCC_FLAGS=-DBXG_TIMERS=1 python -m baryonyx_b200.build --force"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
