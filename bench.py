@@ -371,20 +371,42 @@ def run_engine(args):
             hinst[k] = pinned_like(inst[k])
         h2d = sum(hinst[k].nbytes for k in keys) + 4 * L
         d2h = 0
+        step_seeds = [pinned_like(seeds_of(args.warmup + s)) for s in range(args.steps)]
+
+        def e2e_step(seeds):
+            """What a caller of the C ABI does for one batch: merged constraints
+            and seeds from host memory to a new problem + batch, the run, the
+            best vector and the per-lane results back to the host."""
+            t0 = time.perf_counter()
+            pb2 = capi.Problem(hinst, device=local)
+            t1 = time.perf_counter()
+            bt2 = pb2.batch(L, cp)
+            t2 = time.perf_counter()
+            bt2.begin(seeds, reset_solver=True)
+            t3 = time.perf_counter()
+            out2 = bt2.solve()
+            t4 = time.perf_counter()
+            ln, _, _ = bt2.argbest()
+            xb = bt2.best(ln)
+            upd = bt2.counters()["updates"]
+            nbytes = xb.nbytes + sum(v.nbytes for v in out2.values())
+            t5 = time.perf_counter()
+            bt2.close()
+            pb2.close()
+            t6 = time.perf_counter()
+            if os.environ.get("BENCH_E2E_SPLIT"):
+                print("e2e split ms: problem %.1f batch %.1f begin %.1f solve %.1f results %.1f destroy %.1f"
+                      % tuple(1e3 * (b - a) for a, b in zip((t0, t1, t2, t3, t4, t5), (t1, t2, t3, t4, t5, t6))),
+                      file=sys.stderr, flush=True)
+            return upd, nbytes
+
+        e2e_step(pinned_like(seeds_of(0)))  # untimed warm-up (allocator, first-use costs)
         e2e_updates = 0
         barrier()
         te = time.perf_counter()
         for s in range(args.steps):
-            pb2 = capi.Problem(hinst, device=local)
-            bt2 = pb2.batch(L, cp)
-            bt2.begin(pinned_like(seeds_of(args.warmup + s)), reset_solver=True)
-            out2 = bt2.solve()
-            ln, _, _ = bt2.argbest()
-            xb = bt2.best(ln)
-            e2e_updates += bt2.counters()["updates"]
-            d2h = xb.nbytes + sum(v.nbytes for v in out2.values())
-            bt2.close()
-            pb2.close()
+            upd, d2h = e2e_step(step_seeds[s])
+            e2e_updates += upd
         barrier()
         e2e_wall = time.perf_counter() - te
         te_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")

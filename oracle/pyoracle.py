@@ -344,6 +344,8 @@ def ref(fast: bool = False):
     lib.bxref_std_uniform_u64.restype = C.c_uint64
     lib.bxref_std_normal.argtypes = [C.c_double, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32)]
     lib.bxref_generate_seed.argtypes = [C.c_uint64, C.c_uint, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
+    lib.bxref_solve_b200.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, _i8p, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     lib.bxref_std_pow.argtypes = [C.c_double, C.c_double]
     lib.bxref_std_pow.restype = C.c_double
     lib.bxref_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
@@ -390,6 +392,15 @@ class RefProblem:
 
     def run(self, seed: int) -> "RefRun":
         return RefRun(self, seed)
+
+    def solve_b200(self, seed: int, restarts: int = 1, device: int = 0):
+        """baryonyx::itm::solve_b200 (integration/itm_b200.cpp): the reference's
+        problem and result types over the engine's C ABI."""
+        x = np.zeros(self.n, np.int8)
+        value, rem, loop = C.c_double(), C.c_int(), C.c_int64()
+        st = self.lib.bxref_solve_b200(self.h, seed, restarts, device, x, C.byref(value), C.byref(rem),
+                                       C.byref(loop))
+        return {"status": st, "x": x, "value": value.value, "remaining": rem.value, "loop": loop.value}
 
     def solve(self, seed: int):
         x = np.zeros(self.n, np.int8)
