@@ -43,6 +43,31 @@ fail(int code, const std::string& msg)
                                       cudaGetErrorString(e_));                \
     } while (0)
 
+// Device memory comes from the device's stream-ordered pool, told to keep
+// what is freed: creating and destroying a batch (0.5 GB for the bench's
+// 1024 lanes) costs microseconds instead of the tens of milliseconds a
+// cudaFree / cudaMalloc pair can take, so a caller may build a problem and a
+// batch per solve.  Allocation and release are ordered on the legacy default
+// stream; the create functions synchronise it before a batch's own
+// (non-blocking) stream touches the memory, and every entry point drains that
+// stream before it returns, so nothing is in flight at release.
+inline void
+pool_keep_freed_memory()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return;
+    static bool done[64] = {};
+    if (dev < 0 || dev >= 64 || done[dev])
+        return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 template<typename T>
 struct DevBuf
 {
@@ -52,16 +77,22 @@ struct DevBuf
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf()
+    ~DevBuf() { release(); }
+
+    void release()
     {
         if (p)
-            cudaFree(p);
+            cudaFreeAsync(p, nullptr);
+        p = nullptr;
+        n = 0;
     }
 
     cudaError_t alloc(size_t count)
     {
+        release();
+        pool_keep_freed_memory();
         n = count;
-        return cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        return cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(T) * (count ? count : 1), nullptr);
     }
 
     cudaError_t upload(const std::vector<T>& v)
@@ -151,6 +182,8 @@ struct bxg_batch
 
     ~bxg_batch()
     {
+        if (stream)
+            cudaStreamSynchronize(stream); // nothing in flight when the buffers go back to the pool
         if (ev0)
             cudaEventDestroy(ev0);
         if (ev1)
@@ -733,6 +766,7 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.obj_var = pb->d_obj_var.p;
     d.obj_factor = pb->d_obj_factor.p;
 
+    CUDA_TRY(cudaStreamSynchronize(nullptr)); // allocations complete before other streams use them
     *out = pb.release();
     return BXG_OK;
 }
@@ -898,6 +932,7 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
 
+    CUDA_TRY(cudaStreamSynchronize(nullptr)); // allocations complete before the batch's stream uses them
     *out = b.release();
     return BXG_OK;
 }
@@ -1058,6 +1093,7 @@ run_begin(bxg_batch* b, const uint32_t* h_seeds, const uint32_t* d_x0, const uin
                 rng0[l] = static_cast<uint32_t>(std::stoul(os.str()));
             }
             CUDA_TRY(b->d_x0.alloc(x0.size()));
+            CUDA_TRY(cudaStreamSynchronize(nullptr)); // the batch's stream is non-blocking
             CUDA_TRY(cudaMemcpyAsync(b->d_x0.p, x0.data(), sizeof(uint32_t) * x0.size(),
                                      cudaMemcpyHostToDevice, b->stream));
             CUDA_TRY(cudaMemcpyAsync(b->d_rng0.p, rng0.data(), sizeof(uint32_t) * L,

@@ -175,19 +175,9 @@ struct bxg_population
             return BXG_OK;
         CUDA_TRY(cudaSetDevice(pb->device));
         const size_t n = static_cast<size_t>(count) * words;
-        if (d_x.n < n) {
-            if (d_x.p)
-                cudaFree(d_x.p);
-            d_x.p = nullptr;
+        if (d_x.n < n)
             CUDA_TRY(d_x.alloc(n));
-        }
         if (d_remaining.n < static_cast<size_t>(count)) {
-            if (d_remaining.p)
-                cudaFree(d_remaining.p);
-            if (d_value.p)
-                cudaFree(d_value.p);
-            d_remaining.p = nullptr;
-            d_value.p = nullptr;
             CUDA_TRY(d_remaining.alloc(count));
             CUDA_TRY(d_value.alloc(count));
         }
@@ -471,6 +461,7 @@ bxg_population_create(bxg_problem* pb, const bxg_params* p, uint64_t master_seed
         q->order[i] = i;
     }
     q->sort();
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
     *out = q.release();
     return BXG_OK;
 }
@@ -640,10 +631,8 @@ bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* 
         rng0[l] = engine_state(w.rng);
     }
     if (b->d_x0.n < xn) {
-        if (b->d_x0.p)
-            cudaFree(b->d_x0.p);
-        b->d_x0.p = nullptr;
         CUDA_TRY(b->d_x0.alloc(xn));
+        CUDA_TRY(cudaStreamSynchronize(nullptr)); // the batch's stream is non-blocking
     }
     CUDA_TRY(cudaMemcpyAsync(b->d_x0.p, x0.data(), sizeof(uint32_t) * xn, cudaMemcpyHostToDevice,
                              b->stream));

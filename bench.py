@@ -372,6 +372,7 @@ def run_engine(args):
         h2d = sum(hinst[k].nbytes for k in keys) + 4 * L
         d2h = 0
         step_seeds = [pinned_like(seeds_of(args.warmup + s)) for s in range(args.steps)]
+        split = [0.0] * 6  # ms in: problem create, batch create, begin, solve, results, destroy
 
         def e2e_step(seeds):
             """What a caller of the C ABI does for one batch: merged constraints
@@ -394,13 +395,12 @@ def run_engine(args):
             bt2.close()
             pb2.close()
             t6 = time.perf_counter()
-            if os.environ.get("BENCH_E2E_SPLIT"):
-                print("e2e split ms: problem %.1f batch %.1f begin %.1f solve %.1f results %.1f destroy %.1f"
-                      % tuple(1e3 * (b - a) for a, b in zip((t0, t1, t2, t3, t4, t5), (t1, t2, t3, t4, t5, t6))),
-                      file=sys.stderr, flush=True)
+            for i, (a, b) in enumerate(zip((t0, t1, t2, t3, t4, t5), (t1, t2, t3, t4, t5, t6))):
+                split[i] += 1e3 * (b - a)
             return upd, nbytes
 
         e2e_step(pinned_like(seeds_of(0)))  # untimed warm-up (allocator, first-use costs)
+        split = [0.0] * 6
         e2e_updates = 0
         barrier()
         te = time.perf_counter()
@@ -415,7 +415,9 @@ def run_engine(args):
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
             dist.all_reduce(eu_t, op=dist.ReduceOp.SUM)
         e2e = {"value": eu_t.item() / te_t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * te_t.item() / args.steps}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * te_t.item() / args.steps,
+               "split_ms_per_step": dict(zip(("problem_create", "batch_create", "begin", "solve", "results",
+                                              "destroy"), [round(v / args.steps, 2) for v in split]))}
 
     bt.close()
     pb.close()
