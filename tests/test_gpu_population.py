@@ -9,7 +9,7 @@ import pytest
 from baryonyx_b200 import capi, synth
 from oracle import pyoracle as po
 from tests import util
-from tests.test_population import CASES, population_script, same
+from tests.test_population import CASES, _plain, golden_population, population_script, same
 
 pytestmark = pytest.mark.gpu
 
@@ -144,4 +144,19 @@ def test_optimize_rounds_engine_vs_oracle(name, make, extra, expect_solved):
     op.close()
     pop.close()
     bt.close()
+    pb.close()
+
+
+@pytest.mark.parametrize("name,make,over", CASES, ids=[c[0] for c in CASES])
+def test_population_engine_vs_golden(name, make, over):
+    """bxg_population_* against the committed traces of the compiled reference."""
+    g = golden_population(name)
+    inst = make()
+    cp, q = _params(over)
+    pb = capi.Problem(inst, device=0)
+    for master, want in g["masters"].items():
+        pop = capi.Population(pb, q, int(master), workers=2)
+        got = _plain(population_script(pop, inst["n"], cp.kappa_min, cp.kappa_max, g["steps"], g["data_seed"]))
+        assert got == want, (name, master)
+        pop.close()
     pb.close()

@@ -110,3 +110,35 @@ def test_bit_array_hash_matches_reference():
     for n in (1, 63, 64, 65, 1000):
         x = g.integers(0, 2**63, n // 64 + 1, dtype=np.uint64)
         assert R.bxref_bit_array_hash(n, x) == O.ox_bit_array_hash(n, x)
+
+
+# ---- golden traces of the compiled reference (tests/golden/make_golden_population.py)
+def _plain(o):
+    from tests.golden.make_golden_population import plain
+
+    return plain(o)
+
+
+def golden_population(name):
+    import gzip
+    import json
+
+    path = os.path.join(os.path.dirname(__file__), "golden", f"population_{name}.json.gz")
+    with gzip.open(path, "rb") as f:
+        return json.loads(f.read().decode())
+
+
+@pytest.mark.parametrize("name,make,over", CASES, ids=[c[0] for c in CASES])
+def test_population_oracle_vs_golden(name, make, over):
+    """The C restatement against the committed traces of the reference (runs
+    where /root/reference does not exist)."""
+    g = golden_population(name)
+    inst = make()
+    cp = po.clamp_params(util.params(**over))
+    op = po.OracleProblem(inst)
+    for master, want in g["masters"].items():
+        pop = po.Population(op, int(master), threads=2, params=cp)
+        got = _plain(population_script(pop, inst["n"], cp.kappa_min, cp.kappa_max, g["steps"], g["data_seed"]))
+        assert got == want, (name, master)
+        pop.close()
+    op.close()
