@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="spp", choices=["spp", "scp", "csplib022", "rail-small"])
+    ap.add_argument("--workload", default="spp", choices=["spp", "scp", "csplib022", "telebus", "rail-small", "rail"])
     ap.add_argument("--lanes", type=int, default=1024, help="restarts per GPU per step")
     ap.add_argument("--limit", type=int, default=100, help="sweeps per restart (solver_parameters.limit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -67,6 +67,10 @@ def make_instance(name):
         return synth.scp(), "scp41-shaped 200x1000 set covering (BASELINE configs[0])"
     if name == "csplib022":
         return synth.csplib022(), "csplib022-shaped 30x50000, 101 solver (BASELINE configs[2])"
+    if name == "telebus":
+        return synth.telebus(), "telebus-shaped 1500x7000, Z solver (BASELINE configs[3])"
+    if name == "rail":
+        return synth.rail(), "rail4284-shaped 4284x1092610 (BASELINE configs[4])"
     if name == "rail-small":
         return synth.rail(m=1071, n=273152), "rail4284-shaped at 1/4 scale"
     raise ValueError(name)

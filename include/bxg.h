@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BXG_VERSION 1
+#define BXG_VERSION 2
 
 typedef enum bxg_status
 {
