@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/bxg.h but not exported"
     assert sorted(capi.EXPORTS) == names
-    assert lib.bxg_version() == 1
+    assert lib.bxg_version() == 2
 
 
 def test_default_and_clamp_params_match_oracle():
