@@ -1656,7 +1656,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.zs = b.z_scratch ? b.z_scratch + (size_t)lane_id * b.z_bytes : nullptr;
         L.oR = b.oR + (size_t)lane_id * b.order_cap;
         L.mo = b.mo + (size_t)lane_id * b.order_cap;
-        L.sort_cap = plan.r_in_smem ? plan.sort_cap : 0;
+        L.sort_cap = plan.sort_cap; // (the CTA-wide sort also runs on a scratch in global memory)
         L.all_smem = plan.r_in_smem && plan.pi_in_smem && plan.x_in_smem;
         int bits = 1;
         while ((1 << bits) < 2 * plan.sort_cap)
@@ -2120,10 +2120,9 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     if (bytes() > budget)
         cfg.x_in_smem = 0;
     if (bytes() > budget) {
-        // rows too long for the shared-memory sort: scratch in global memory,
-        // single-thread ordering only
+        // rows too long for a shared-memory scratch: it goes to global memory
+        // (L2-resident, a few hundred KB per lane); the CTA-wide sort runs there
         cfg.r_in_smem = 0;
-        cfg.sort_cap = pb.max_row;
     }
     if (bytes() > budget)
         cfg.pi_in_smem = 0;
