@@ -76,6 +76,8 @@ EXPORTS = [
     "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
     "bxg_population_mutation", "bxg_population_try_update", "bxg_population_try_advance",
     "bxg_population_score", "bxg_optimize_round", "bxg_bit_array_hash",
+    "bxg_lp_read", "bxg_lp_parse", "bxg_lp_destroy", "bxg_lp_info", "bxg_lp_rows", "bxg_lp_objective",
+    "bxg_lp_variable",
 ]
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -432,3 +434,44 @@ class Population:
         if self.h:
             lib().bxg_population_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def read_lp(path: str | None = None, text: str | None = None, pre_order: int = 0) -> dict:
+    """LP file (or text) -> the instance dict Problem takes: the engine's own
+    reader + constraint merging (bxg_lp_*), no device needed."""
+    L = lib()
+    L.bxg_lp_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.bxg_lp_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.bxg_lp_destroy.argtypes = [C.c_void_p]
+    L.bxg_lp_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.bxg_lp_rows.argtypes = [C.c_void_p, _i32p, _i32p, _i32p, _i32p, _i32p]
+    L.bxg_lp_objective.argtypes = [C.c_void_p, _i32p, _f64p]
+    L.bxg_lp_variable.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+    L.bxg_lp_variable.restype = C.c_char_p
+    h = C.c_void_p()
+    if path is not None:
+        check(L.bxg_lp_read(path.encode(), pre_order, C.byref(h)))
+    else:
+        raw = text.encode()
+        check(L.bxg_lp_parse(raw, len(raw), pre_order, C.byref(h)))
+    try:
+        v = [C.c_int() for _ in range(5)]
+        cc, nobj = C.c_double(), C.c_int()
+        check(L.bxg_lp_info(h, *[C.byref(a) for a in v], C.byref(cc), C.byref(nobj)))
+        m, n, nnz, ptype, maximize = [a.value for a in v]
+        row_ptr = np.zeros(m + 1, np.int32)
+        col, fac = np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.int32)
+        cmin, cmax = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32)
+        check(L.bxg_lp_rows(h, row_ptr, col, fac, cmin, cmax))
+        ov, of = np.zeros(max(nobj.value, 1), np.int32), np.zeros(max(nobj.value, 1), np.float64)
+        check(L.bxg_lp_objective(h, ov, of))
+        names, bounds = [], []
+        for i in range(n):
+            lo, hi, ty = C.c_int(), C.c_int(), C.c_int()
+            names.append(L.bxg_lp_variable(h, i, C.byref(lo), C.byref(hi), C.byref(ty)).decode())
+            bounds.append((lo.value, hi.value, ty.value))
+        return {"m": m, "n": n, "row_ptr": row_ptr, "col": col[:nnz], "factor": fac[:nnz], "cmin": cmin[:m],
+                "cmax": cmax[:m], "problem_type": ptype, "maximize": maximize, "obj_var": ov[: nobj.value],
+                "obj_factor": of[: nobj.value], "cost_constant": cc.value, "names": names, "bounds": bounds}
+    finally:
+        L.bxg_lp_destroy(h)

@@ -1500,4 +1500,5 @@ bxg_batch_launches(bxg_batch* b, int64_t* launches)
 
 } // extern "C"
 
+#include "bxg_lp.hpp"
 #include "bxg_population.cuh"

@@ -14,6 +14,7 @@
 #ifndef BXG_H
 #define BXG_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -298,6 +299,32 @@ int bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round,
                        int32_t* status, double* value, int32_t* remaining);
 /* bit_array_hash, bit-array.hpp:410-423 */
 uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
+
+/* ---- LP reader ---------------------------------------------------------------
+ * From LP text to the arguments of bxg_problem_create: what the reference
+ * obtains with make_problem (lib/src/parser.cpp:1065-1273), problem(raw_problem)
+ * (lib/src/problem.hpp:58-122) and make_merged_constraints
+ * (lib/src/merged-constraint.cpp:52-175,297-343).  Same dialect and the same
+ * conventions: variables numbered by first appearance, coefficients and
+ * right-hand sides truncated to int, rows over the same elements merged into
+ * one [min, max] row, rows in file order.  pre_order: 0 = none, 1 = memory
+ * (elements of a row sorted by variable), the reference's other orders are
+ * BXG_E_INVALID; so are quadratic objectives.  Host code, no device needed.
+ * On a malformed file bxg_last_error() carries the reference's
+ * file_format_error_tag name. */
+typedef struct bxg_lp bxg_lp;
+int bxg_lp_read(const char* path, int pre_order, bxg_lp** out);
+int bxg_lp_parse(const char* text, size_t length, int pre_order, bxg_lp** out);
+void bxg_lp_destroy(bxg_lp* lp);
+int bxg_lp_info(const bxg_lp* lp, int* m, int* n, int* nnz, int* problem_type,
+                int* maximize, double* cost_constant, int* n_obj);
+/* row_ptr[m+1], col / factor[nnz], cmin / cmax[m] (INT_MIN / INT_MAX: open side) */
+int bxg_lp_rows(const bxg_lp* lp, int32_t* row_ptr, int32_t* col,
+                int32_t* factor, int32_t* cmin, int32_t* cmax);
+/* objective elements in the order of first appearance */
+int bxg_lp_objective(const bxg_lp* lp, int32_t* obj_var, double* obj_factor);
+/* name (owned by the handle), bounds and variable_type (0 real, 1 binary, 2 general) */
+const char* bxg_lp_variable(const bxg_lp* lp, int i, int* min, int* max, int* type);
 
 #ifdef __cplusplus
 }

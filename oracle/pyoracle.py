@@ -390,6 +390,18 @@ class RefProblem:
             "obj_var": ov[: self.n_obj], "obj_factor": of[: self.n_obj], "cost_constant": self.cost_constant,
         }
 
+    def variables(self):
+        """(names, [(min, max, variable_type)]) of the parsed problem."""
+        f = self.lib.bxref_variable
+        f.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+        f.restype = C.c_char_p
+        names, bounds = [], []
+        for i in range(self.n):
+            lo, hi, ty = C.c_int(), C.c_int(), C.c_int()
+            names.append(f(self.h, i, C.byref(lo), C.byref(hi), C.byref(ty)).decode())
+            bounds.append((lo.value, hi.value, ty.value))
+        return names, bounds
+
     def run(self, seed: int) -> "RefRun":
         return RefRun(self, seed)
 

@@ -77,6 +77,9 @@ int bxref_export_rows(void* h, int* row_ptr, int* col, int* factor, int* cmin,
                       int* cmax);
 /* objective elements in file order */
 int bxref_export_objective(void* h, int* var, double* factor);
+/* variable i of the parsed problem: name (valid until the next call on this
+ * thread), bounds, baryonyx::variable_type value */
+const char* bxref_variable(void* h, int i, int* min, int* max, int* type);
 
 /* Step-level run (replicates the set-up of solver_functor::operator(),
  * lib/src/itm-solver-common.hpp:63-133, with the reference's own Solver and

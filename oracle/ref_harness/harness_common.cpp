@@ -304,6 +304,20 @@ bxref_export_objective(void* hv, int* var, double* factor)
     return 0;
 }
 
+const char*
+bxref_variable(void* hv, int i, int* min, int* max, int* type)
+{
+    auto* h = static_cast<bxref::handle*>(hv);
+    if (i < 0 || i >= length(h->pb.vars.values))
+        return nullptr;
+    thread_local std::string name;
+    name.assign(h->pb.vars.names[i].data(), h->pb.vars.names[i].size());
+    *min = h->pb.vars.values[i].min;
+    *max = h->pb.vars.values[i].max;
+    *type = static_cast<int>(h->pb.vars.values[i].type);
+    return name.c_str();
+}
+
 #define BXREF_DISPATCH(h, CALL)                                               \
     switch ((h)->pb.problem_type) {                                           \
     case problem_solver_type::equalities_01:                                  \

@@ -1,0 +1,204 @@
+"""The engine's LP reader (bxg_lp_*, include/bxg.h) against the reference's
+make_problem + make_merged_constraints (lib/src/parser.cpp:1065-1273,
+lib/src/merged-constraint.cpp:297-343): same variable numbering, rows, bounds,
+objective and solver family.  Host code: these run without a GPU; the last
+test feeds a parsed file to the CUDA engine (-m gpu)."""
+import ctypes as C
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from baryonyx_b200 import capi, synth
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LP_DIR = os.path.join(ROOT, "tests", "golden", "lp")
+REF_DIR = "/root/reference"
+INT_MIN, INT_MAX = -(2**31), 2**31 - 1
+ARRAYS = ("row_ptr", "col", "factor", "cmin", "cmax", "obj_var", "obj_factor")
+SCALARS = ("m", "n", "problem_type", "maximize", "cost_constant")
+
+
+def same_parse(mine: dict, want: dict, what):
+    for k in SCALARS:
+        assert mine[k] == want[k], (what, k, mine[k], want[k])
+    for k in ARRAYS:
+        a, b = np.asarray(mine[k]), np.asarray(want[k])
+        assert a.shape == b.shape and np.array_equal(a, b), (what, k)
+    if "names" in want:
+        assert mine["names"] == list(want["names"]), (what, "names")
+        assert [tuple(b) for b in mine["bounds"]] == [tuple(b) for b in want["bounds"]], (what, "bounds")
+
+
+GOLDEN = sorted(glob.glob(os.path.join(LP_DIR, "*.lp")))
+
+
+def test_golden_lp_fixtures_present():
+    assert len(GOLDEN) >= 4
+    for lp in GOLDEN:
+        assert os.path.exists(lp[:-3] + ".json"), lp
+
+
+@pytest.mark.parametrize("lp", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+@pytest.mark.parametrize("pre_order", [0, 1])
+def test_reader_matches_reference_golden(lp, pre_order):
+    want = json.load(open(lp[:-3] + ".json"))[f"pre_order_{pre_order}"]
+    same_parse(capi.read_lp(path=lp, pre_order=pre_order), want, lp)
+    # same text through the in-memory entry point
+    same_parse(capi.read_lp(text=open(lp).read(), pre_order=pre_order), want, lp)
+
+
+def test_named_objective():
+    """lib/test/io.cpp:42-61"""
+    d = capi.read_lp(text="maximize\nx0: +x1 + 2x2 + 3x3 - 100\nend\n")
+    assert d["maximize"] == 1 and d["m"] == 0 and d["n"] == 3
+    assert d["obj_var"].tolist() == [0, 1, 2] and d["obj_factor"].tolist() == [1.0, 2.0, 3.0]
+    assert d["cost_constant"] == -100.0
+    assert d["names"] == ["x1", "x2", "x3"]
+
+
+def test_unnamed_objective_goes_to_constraints():
+    """lib/test/io.cpp:63-80"""
+    d = capi.read_lp(text="maximize\nst: x1 + x2 + x3 = 1\nend\n")
+    assert d["maximize"] == 1 and len(d["obj_var"]) == 0
+    assert d["n"] == 3 and d["m"] == 1
+    assert d["col"].tolist() == [0, 1, 2] and d["factor"].tolist() == [1, 1, 1]
+    assert d["cmin"].tolist() == [1] and d["cmax"].tolist() == [1]
+
+
+def test_small_lp():
+    """lib/test/io.cpp:82-150; the two rows over x1 - 3x2 + x3 merge into one
+    (merged-constraint.cpp:52-175: the tighter bound wins)."""
+    text = ("maximize\nobj: x1 + 2x2 + 3x3 - 100\nst\ntime:  -x1 + x2 + x3 <= 20\n"
+            "labor:  x1 - 3x2 + x3 <= 30\ntest: x1 - 3x2 + x3 <= -5\nbounds\nx1 <= 40\nend\n")
+    d = capi.read_lp(text=text)
+    assert d["obj_factor"].tolist() == [1.0, 2.0, 3.0] and d["cost_constant"] == -100.0
+    assert d["names"] == ["x1", "x2", "x3"]
+    assert [b[0] for b in d["bounds"]] == [0, 0, 0]
+    assert [b[1] for b in d["bounds"]] == [40, INT_MAX, INT_MAX]
+    assert d["m"] == 2
+    assert d["factor"].tolist() == [-1, 1, 1, 1, -3, 1]
+    assert d["cmin"].tolist() == [INT_MIN, INT_MIN] and d["cmax"].tolist() == [20, -5]
+
+
+@pytest.mark.parametrize("text, tag, reference", [
+    ("", "bad_objective_function_type", "refuses"),
+    ("minimise\n x + y\nend\n", "bad_objective_function_type", "refuses"),
+    # no right-hand side: the reference's pop_front(0) contract calls std::terminate
+    # (parser.cpp:302); behind a C ABI that is an error return
+    ("minimize\n x + y\nst\n c: x + y <= \nend\n", "bad_constraint", "aborts"),
+    ("minimize\n x + y\nst\n c: x + y <= 1\nbounds\n x <= \nend\n", "bad_bound", "refuses"),
+    # a variable called e reads as a number in the bounds section (parser.cpp read_real / sscanf)
+    ("minimize\n a + e\nst\n c: a + e <= 1\nbounds\n e <= 1\nend\n", "bad_bound", "refuses"),
+    # the general section comes after the binary section in this dialect
+    ("minimize\n a + b\nst\n c: a + b <= 1\ngeneral\n a\nbinary\n b\nend\n", "bad_end", "refuses"),
+    ("minimize\n x + y\nst\n c: x + y <= 1\n", "bad_end", "refuses"),
+    # quadratic objectives parse in the reference; no solver of this path takes them
+    ("minimize\n x + [ x * y ] / 2\nst\n c: x + y <= 1\nend\n", "quadratic", "accepts"),
+])
+def test_malformed_text_is_refused_with_the_reference_tag(text, tag, reference, tmp_path):
+    with pytest.raises(capi.BxgError) as e:
+        capi.read_lp(text=text)
+    assert tag in str(e.value), str(e.value)
+    assert e.value.code == -1  # BXG_E_INVALID
+    if po.ref_available() and reference == "refuses":
+        f = tmp_path / "bad.lp"
+        f.write_text(text)
+        with pytest.raises(RuntimeError):
+            po.RefProblem(str(f), po.default_params())
+
+
+def test_missing_file():
+    with pytest.raises(capi.BxgError) as e:
+        capi.read_lp(path="/nonexistent/file.lp")
+    assert "file_not_found" in str(e.value)
+
+
+def test_unsupported_pre_order():
+    with pytest.raises(capi.BxgError):
+        capi.read_lp(text="minimize\n x\nst\n c: x <= 1\nend\n", pre_order=2)
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.small_mixed(family="01", equality=True, seed=11),
+    lambda: synth.small_mixed(family="101", seed=12),
+    lambda: synth.small_mixed(family="Z", seed=13, maximize=True),
+    lambda: synth.scp(),
+    lambda: synth.spp(m=100, n=2000),
+    lambda: synth.telebus(m=150, n=700),
+])
+def test_write_then_read_round_trip(make, tmp_path):
+    """synth.write_lp -> bxg_lp_read returns the instance it was written from
+    (size-independent property; BASELINE-shaped generators included)."""
+    inst = make()
+    path = synth.write_lp(inst, str(tmp_path / "rt.lp"))
+    d = capi.read_lp(path=path)
+    assert d["n"] == inst["n"] and d["maximize"] == inst["maximize"]
+    assert d["problem_type"] == inst["problem_type"]
+    cost = np.zeros(inst["n"])
+    np.add.at(cost, np.asarray(inst["obj_var"]), np.asarray(inst["obj_factor"]))
+    mine = np.zeros(inst["n"])
+    np.add.at(mine, d["obj_var"], d["obj_factor"])
+    assert np.array_equal(cost, mine)
+    for k in ("m", "row_ptr", "col", "factor", "cmin", "cmax"):
+        assert np.array_equal(np.asarray(d[k]), np.asarray(inst[k])), k
+    assert all(b == (0, 1, 1) for b in d["bounds"])
+
+
+REF_LPS = sorted(glob.glob(os.path.join(REF_DIR, "**", "*.lp"), recursive=True))
+
+
+@pytest.mark.skipif(not (REF_LPS and po.ref_available()), reason="needs /root/reference and oracle/_ref (build container)")
+def test_every_reference_fixture_parses_like_the_reference():
+    """All LP files the reference ships (lib/test/*.lp and the rest), both
+    supported constraint orders, against the compiled reference's parser."""
+    assert len(REF_LPS) >= 50
+    compared = 0
+    for lp in REF_LPS:
+        for pre_order in (0, 1):
+            p = po.default_params()
+            p.pre_order = pre_order
+            try:
+                r = po.RefProblem(lp, p)
+            except RuntimeError:
+                with pytest.raises(capi.BxgError):
+                    capi.read_lp(path=lp, pre_order=pre_order)
+                continue
+            want = r.instance()
+            want["names"], want["bounds"] = r.variables()
+            r.close()
+            same_parse(capi.read_lp(path=lp, pre_order=pre_order), want, (lp, pre_order))
+            compared += 1
+    assert compared >= 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lp", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_parsed_file_solves_like_the_oracle(lp):
+    """LP text -> bxg_lp_* -> bxg_problem_create -> solve on the device equals
+    the oracle on the golden parse of the same file."""
+    inst = capi.read_lp(path=lp)
+    want = json.load(open(lp[:-3] + ".json"))["pre_order_0"]
+    oinst = {k: (np.asarray(v, np.float64 if k == "obj_factor" else np.int32) if k in ARRAYS else v)
+             for k, v in want.items()}
+    p = po.default_params()
+    p.limit = 200
+    q = capi.Params()
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+    seeds = [3, 17, 123456]
+    op = po.OracleProblem(oinst)
+    pb = capi.Problem(inst)
+    bt = pb.batch(len(seeds), q)
+    bt.begin(seeds)
+    out = bt.solve()
+    for lane, seed in enumerate(seeds):
+        sol = op.solve(p, seed)
+        assert int(out["status"][lane]) == sol["status"], (lp, lane)
+        if sol["status"] == 0:
+            assert np.array_equal(out["x"][lane], sol["x"]), (lp, lane)
+            assert float(out["value"][lane]) == sol["value"], (lp, lane)
+    op.close()
+    pb.close()

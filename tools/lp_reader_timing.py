@@ -1,0 +1,61 @@
+"""time bxg_lp_read against the compiled reference's
+make_problem + make_merged_constraints (oracle/_ref) on the same LP text.
+Host code on one core each; build container only (needs oracle/_ref).
+
+    python tools/lp_reader_timing.py [m n]      # rail-shaped instance, default 2000 x 200000
+"""
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from baryonyx_b200 import capi, synth  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+
+def timed(f, reps=3):
+    best = float("inf")
+    for _ in range(reps):
+        t = time.perf_counter()
+        out = f()
+        best = min(best, time.perf_counter() - t)
+    return best, out
+
+
+def main():
+    m, n = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) == 3 else (2000, 200000)
+    inst = synth.rail(m=m, n=n)
+    path = synth.write_lp(inst, os.path.join(tempfile.mkdtemp(), "rail.lp"))
+    size = os.path.getsize(path)
+    import ctypes as C
+
+    def mine():
+        h = C.c_void_p()
+        capi.check(capi.lib().bxg_lp_read(path.encode(), 0, C.byref(h)))
+        capi.lib().bxg_lp_destroy.argtypes = [C.c_void_p]
+        capi.lib().bxg_lp_destroy(h)
+
+    def ref():
+        r = po.RefProblem(path, po.default_params())
+        r.close()
+
+    d = capi.read_lp(path=path)
+    r = po.RefProblem(path, po.default_params())
+    want = r.instance()
+    r.close()
+    for k in ("row_ptr", "col", "factor", "cmin", "cmax", "obj_var", "obj_factor"):
+        assert np.array_equal(d[k], want[k]), k
+    t_mine, _ = timed(mine)
+    t_ref, _ = timed(ref)
+    print({"file_MB": round(size / 1e6, 1), "m": d["m"], "n": d["n"], "nnz": int(d["row_ptr"][-1]),
+           "bxg_lp_read_s": round(t_mine, 3), "reference_s": round(t_ref, 3),
+           "MB_per_s": round(size / 1e6 / t_mine, 1), "ratio": round(t_ref / t_mine, 2)})
+
+
+if __name__ == "__main__":
+    main()
