@@ -198,7 +198,8 @@ def test_parsed_file_solves_like_the_oracle(lp):
         sol = op.solve(p, seed)
         assert int(out["status"][lane]) == sol["status"], (lp, lane)
         if sol["status"] == 0:
-            assert np.array_equal(out["x"][lane], sol["x"]), (lp, lane)
+            assert np.array_equal(bt.best(lane), sol["x"]), (lp, lane)
             assert float(out["value"][lane]) == sol["value"], (lp, lane)
+    bt.close()
     op.close()
     pb.close()
