@@ -18,6 +18,7 @@
 
 #include <cctype>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <string_view>
 #include <unordered_map>
@@ -37,41 +38,62 @@ same_word(std::string_view a, std::string_view b)
     return true;
 }
 
+// Character classes of the dialect (parser.cpp: is_separator, is_char_name,
+// is_number / number continuation), one table lookup per character.
+enum : unsigned char { C_SPACE = 1, C_SEP = 2, C_NAME = 4, C_NUM = 8, C_NUM0 = 16 };
+
+struct char_table
+{
+    unsigned char cls[256] = {};
+
+    char_table()
+    {
+        for (int c = 0; c < 256; ++c) {
+            unsigned char k = 0;
+            if (std::isspace(c))
+                k |= C_SPACE;
+            if (std::strchr("<=>:-+[]*^", c) && c)
+                k |= C_SEP;
+            if ((c < 128 && std::isalnum(c)) || (c && std::strchr("!\"#$%&(),.;?@_{}~", c)))
+                k |= C_NAME;
+            if ((c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+')
+                k |= C_NUM | C_NUM0;
+            if (c == 'e' || c == 'E')
+                k |= C_NUM;
+            cls[c] = k;
+        }
+    }
+};
+
+inline const unsigned char*
+classes()
+{
+    static const char_table t;
+    return t.cls;
+}
+
 inline bool
 is_separator(int c)
 {
-    switch (c) {
-    case '<': case '=': case '>': case ':': case '-': case '+': case '[': case ']': case '*': case '^':
-        return true;
-    default:
-        return false;
-    }
+    return classes()[static_cast<unsigned char>(c)] & C_SEP;
 }
 
 inline bool
 is_name_char(int c)
 {
-    if (std::isalnum(static_cast<unsigned char>(c)) && c < 128)
-        return true;
-    switch (c) {
-    case '!': case '"': case '#': case '$': case '%': case '&': case '(': case ')': case ',': case '.':
-    case ';': case '?': case '@': case '_': case '{': case '}': case '~':
-        return true;
-    default:
-        return false;
-    }
+    return classes()[static_cast<unsigned char>(c)] & C_NAME;
 }
 
 inline bool
 is_number_char(int c)
 {
-    return (c >= '0' && c <= '9') || c == '.' || c == 'e' || c == 'E' || c == '-' || c == '+';
+    return classes()[static_cast<unsigned char>(c)] & C_NUM;
 }
 
 inline bool
 starts_number(int c)
 {
-    return (c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+';
+    return classes()[static_cast<unsigned char>(c)] & C_NUM0;
 }
 
 inline bool
@@ -97,14 +119,16 @@ struct tokens
     {
         const char* s = text.data();
         const size_t n = text.size();
+        const unsigned char* cls = classes();
+        tok.reserve(n / 3 + 16);
         size_t i = 0;
         while (i < n) {
-            while (i < n && std::isspace(static_cast<unsigned char>(s[i])))
+            while (i < n && (cls[static_cast<unsigned char>(s[i])] & C_SPACE))
                 ++i;
             if (i == n)
                 break;
             size_t e = i;
-            while (e < n && !std::isspace(static_cast<unsigned char>(s[e])))
+            while (e < n && !(cls[static_cast<unsigned char>(s[e])] & C_SPACE))
                 ++e;
             if (s[i] == '\\') { // comment: the rest of the line
                 while (e < n && s[e] != '\n')
@@ -122,18 +146,20 @@ struct tokens
     void split(size_t b, size_t e)
     {
         const char* s = text.data();
+        const unsigned char* cls = classes();
         size_t cur = b;
         while (cur < e) {
-            const bool number = starts_number(s[cur]);
+            const unsigned char k0 = cls[static_cast<unsigned char>(s[cur])];
             const size_t start = cur++;
-            if (is_separator(s[start]) || cur == e) {
+            if ((k0 & C_SEP) || cur == e) {
                 tok.emplace_back(s + start, 1);
                 continue;
             }
+            // a number stops where a number cannot go on, anything stops at a separator
+            const unsigned char stop = C_SEP, need = (k0 & C_NUM0) ? C_NUM : 0;
             while (cur < e) {
-                if (is_separator(s[cur]))
-                    break;
-                if (number && !is_number_char(s[cur]))
+                const unsigned char k = cls[static_cast<unsigned char>(s[cur])];
+                if ((k & stop) || (k & need) != need)
                     break;
                 ++cur;
             }
@@ -154,6 +180,23 @@ read_real(std::string_view s, double& v)
     }
     if (s.empty() || s.size() > 320)
         return false;
+    {
+        // strtod can only succeed on [+-] digit . inf nan; plain digit strings
+        // below 2^53 convert exactly without it
+        const char c = s[0];
+        if (!((c >= '0' && c <= '9') || c == '.' || c == '+' || c == '-' || c == 'i' || c == 'I' || c == 'n' || c == 'N'))
+            return false;
+        if (s.size() <= 15) {
+            uint64_t acc = 0;
+            size_t i = 0;
+            for (; i != s.size() && s[i] >= '0' && s[i] <= '9'; ++i)
+                acc = acc * 10 + static_cast<uint64_t>(s[i] - '0');
+            if (i == s.size()) {
+                v = static_cast<double>(acc);
+                return true;
+            }
+        }
+    }
     const std::string z(s);
     char* end = nullptr;
     const double r = std::strtod(z.c_str(), &end); // sscanf("%lf") of the reference
@@ -249,6 +292,73 @@ read_operator(std::string_view a, std::string_view b, int& op)
     return 0;
 }
 
+// Variable names -> ids: open addressing over (hash, id), names compared
+// through the views kept in `keys` (views into the token text).
+struct name_table
+{
+    std::vector<uint64_t> slot; // (hash & ~mask_id) | (id + 1), 0 = free
+    std::vector<std::string_view> keys;
+    size_t mask = 0;
+
+    static uint64_t hash(std::string_view s)
+    {
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ s.size();
+        const char* p = s.data();
+        size_t n = s.size();
+        while (n >= 8) {
+            uint64_t w;
+            std::memcpy(&w, p, 8);
+            h = (h ^ w) * 0xff51afd7ed558ccdull;
+            h ^= h >> 32;
+            p += 8, n -= 8;
+        }
+        uint64_t w = 0;
+        std::memcpy(&w, p, n);
+        h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+        return h ^ (h >> 29);
+    }
+
+    void grow()
+    {
+        const size_t cap = slot.empty() ? 1024 : slot.size() * 2;
+        std::vector<uint64_t> next(cap, 0);
+        mask = cap - 1;
+        for (size_t id = 0; id != keys.size(); ++id) {
+            const uint64_t h = hash(keys[id]);
+            size_t i = h & mask;
+            while (next[i])
+                i = (i + 1) & mask;
+            next[i] = (h << 32) | (id + 1);
+        }
+        slot.swap(next);
+    }
+
+    // id of `name`, or -1 (insert = false) / a fresh id (insert = true; fresh set)
+    int find(std::string_view name, bool insert, bool& fresh)
+    {
+        fresh = false;
+        if ((keys.size() + 1) * 2 > slot.size())
+            grow();
+        const uint64_t h = hash(name);
+        size_t i = h & mask;
+        while (slot[i]) {
+            if ((slot[i] >> 32) == (h & 0xffffffffull)) {
+                const int id = static_cast<int>(slot[i] & 0xffffffffull) - 1;
+                if (keys[id] == name)
+                    return id;
+            }
+            i = (i + 1) & mask;
+        }
+        if (!insert)
+            return -1;
+        const int id = static_cast<int>(keys.size());
+        keys.push_back(name);
+        slot[i] = (h << 32) | static_cast<uint64_t>(id + 1);
+        fresh = true;
+        return id;
+    }
+};
+
 struct row
 {
     std::vector<std::pair<int, int>> elements; // (factor, variable)
@@ -288,19 +398,20 @@ std::string
 lp_parse(std::string text, bxg_lp& out)
 {
     lp::tokens t(std::move(text));
-    std::unordered_map<std::string_view, int> ids;
+    lp::name_table ids;
     // where[v] = (owner, position): v's element in the objective (owner -2) or
     // in the row being read (owner = its id); anything else means "not yet"
     std::vector<std::pair<int, int>> where;
     auto variable = [&](std::string_view name) { // keys are views into t.text, alive for the whole parse
-        auto [it, fresh] = ids.try_emplace(name, static_cast<int>(out.vars.size()));
+        bool fresh;
+        const int id = ids.find(name, true, fresh);
         if (fresh)
             out.vars.push_back({ std::string(name) });
-        return it->second;
+        return id;
     };
     auto known = [&](std::string_view name) {
-        auto it = ids.find(name);
-        return it == ids.end() ? -1 : it->second;
+        bool fresh;
+        return ids.find(name, false, fresh);
     };
 
     const std::string_view head = t.at(0);
