@@ -19,6 +19,7 @@
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
 #include <fstream>
 #include <string_view>
 #include <unordered_map>
@@ -292,12 +293,53 @@ read_operator(std::string_view a, std::string_view b, int& op)
     return 0;
 }
 
-// Variable names -> ids: open addressing over (hash, id), names compared
-// through the views kept in `keys` (views into the token text).
+// Allocator of the big look-up table: 2 MB alignment + MADV_HUGEPAGE, so that
+// random probes of a table of tens of MB do not pay a TLB miss each.
+template<typename T>
+struct huge_allocator
+{
+    using value_type = T;
+    huge_allocator() = default;
+    template<typename U>
+    huge_allocator(const huge_allocator<U>&) {}
+    T* allocate(size_t n)
+    {
+        constexpr size_t huge = size_t(2) << 20;
+        size_t bytes = n * sizeof(T);
+        void* p = nullptr;
+        if (bytes >= huge) {
+            bytes = (bytes + huge - 1) / huge * huge;
+            if (posix_memalign(&p, huge, bytes) != 0)
+                throw std::bad_alloc();
+            madvise(p, bytes, MADV_HUGEPAGE);
+        } else if (!(p = std::malloc(bytes ? bytes : 1)))
+            throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { std::free(p); }
+    template<typename U>
+    bool operator==(const huge_allocator<U>&) const { return true; }
+    template<typename U>
+    bool operator!=(const huge_allocator<U>&) const { return false; }
+};
+
+// Variable names -> ids.  Open addressing; an entry carries the name itself
+// (up to 19 characters inline, longer ones through `keys`) and the variable's
+// (owner, position) stamp, so that a look-up touches one cache line; the
+// parser prefetches the entries of the names a few elements ahead.
 struct name_table
 {
-    std::vector<uint64_t> slot; // (hash & ~mask_id) | (id + 1), 0 = free
-    std::vector<std::string_view> keys;
+    struct entry
+    {
+        int32_t id = -1; // -1: free
+        int32_t owner = -1, position = 0;
+        uint8_t len = 0; // 255: longer than the inline room
+        char name[19];
+    };
+    static_assert(sizeof(entry) == 32, "two entries per cache line");
+
+    std::vector<entry, huge_allocator<entry>> slot;
+    std::vector<std::string_view> keys; // id -> name (views into the token text)
     size_t mask = 0;
 
     static uint64_t hash(std::string_view s)
@@ -314,48 +356,67 @@ struct name_table
         }
         uint64_t w = 0;
         std::memcpy(&w, p, n);
-        h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
-        return h ^ (h >> 29);
+        h ^= w;
+        // full avalanche: names that differ in their last characters only
+        // must not share the low (index) bits
+        h ^= h >> 33;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 33;
+        h *= 0xc4ceb9fe1a85ec53ull;
+        return h ^ (h >> 33);
     }
 
     void grow()
     {
-        const size_t cap = slot.empty() ? 1024 : slot.size() * 2;
-        std::vector<uint64_t> next(cap, 0);
+        const size_t cap = slot.empty() ? 2048 : slot.size() * 2;
+        std::vector<entry, huge_allocator<entry>> next(cap);
         mask = cap - 1;
-        for (size_t id = 0; id != keys.size(); ++id) {
-            const uint64_t h = hash(keys[id]);
-            size_t i = h & mask;
-            while (next[i])
+        for (const entry& e : slot) {
+            if (e.id < 0)
+                continue;
+            size_t i = hash(keys[e.id]) & mask;
+            while (next[i].id >= 0)
                 i = (i + 1) & mask;
-            next[i] = (h << 32) | (id + 1);
+            next[i] = e;
         }
         slot.swap(next);
     }
 
-    // id of `name`, or -1 (insert = false) / a fresh id (insert = true; fresh set)
-    int find(std::string_view name, bool insert, bool& fresh)
+    void prefetch(std::string_view name) const
+    {
+        if (mask)
+            __builtin_prefetch(&slot[hash(name) & mask]);
+    }
+
+    // entry of `name`; nullptr when absent and !insert; fresh set when inserted
+    entry* find(std::string_view name, bool insert, bool& fresh)
     {
         fresh = false;
         if ((keys.size() + 1) * 2 > slot.size())
             grow();
-        const uint64_t h = hash(name);
-        size_t i = h & mask;
-        while (slot[i]) {
-            if ((slot[i] >> 32) == (h & 0xffffffffull)) {
-                const int id = static_cast<int>(slot[i] & 0xffffffffull) - 1;
-                if (keys[id] == name)
-                    return id;
-            }
+        const size_t n = name.size();
+        size_t i = hash(name) & mask;
+        while (slot[i].id >= 0) {
+            entry& e = slot[i];
+            if (n <= sizeof(e.name) ? (e.len == n && std::memcmp(e.name, name.data(), n) == 0)
+                                    : (e.len == 255 && keys[e.id] == name))
+                return &e;
             i = (i + 1) & mask;
         }
         if (!insert)
-            return -1;
-        const int id = static_cast<int>(keys.size());
+            return nullptr;
+        entry& e = slot[i];
+        e.id = static_cast<int32_t>(keys.size());
+        e.owner = -1;
+        e.position = 0;
+        if (n <= sizeof(e.name)) {
+            e.len = static_cast<uint8_t>(n);
+            std::memcpy(e.name, name.data(), n);
+        } else
+            e.len = 255;
         keys.push_back(name);
-        slot[i] = (h << 32) | static_cast<uint64_t>(id + 1);
         fresh = true;
-        return id;
+        return &e;
     }
 };
 
@@ -399,19 +460,27 @@ lp_parse(std::string text, bxg_lp& out)
 {
     lp::tokens t(std::move(text));
     lp::name_table ids;
-    // where[v] = (owner, position): v's element in the objective (owner -2) or
-    // in the row being read (owner = its id); anything else means "not yet"
-    std::vector<std::pair<int, int>> where;
+    // an entry's (owner, position): the variable's element in the objective
+    // (owner -2) or in the row being read (owner = its id); else "not yet"
     auto variable = [&](std::string_view name) { // keys are views into t.text, alive for the whole parse
         bool fresh;
-        const int id = ids.find(name, true, fresh);
+        lp::name_table::entry* e = ids.find(name, true, fresh);
         if (fresh)
             out.vars.push_back({ std::string(name) });
-        return id;
+        return e;
     };
     auto known = [&](std::string_view name) {
         bool fresh;
-        return ids.find(name, false, fresh);
+        const lp::name_table::entry* e = ids.find(name, false, fresh);
+        return e ? e->id : -1;
+    };
+    // names some elements ahead: bring their table entries into cache
+    auto look_ahead = [&]() {
+        const std::string_view a = t.at(24), b = t.at(25);
+        if (a.size() > 1 || (!a.empty() && !lp::is_separator(a[0])))
+            ids.prefetch(a);
+        if (b.size() > 1 || (!b.empty() && !lp::is_separator(b[0])))
+            ids.prefetch(b);
     };
 
     const std::string_view head = t.at(0);
@@ -437,14 +506,14 @@ lp_parse(std::string text, bxg_lp& out)
             // (the reference looks a repeated variable up with a linear find_if,
             // parser.cpp:1085-1097: quadratic in the objective's length; a
             // per-variable position gives the same result in O(1))
-            const int id = variable(e.name);
-            if (static_cast<size_t>(id) >= where.size())
-                where.resize(out.vars.size() + out.vars.size() / 2 + 16, { -1, 0 });
-            if (where[id].first != -2) {
-                where[id] = { -2, static_cast<int>(out.objective.size()) };
-                out.objective.emplace_back(e.factor, id);
+            look_ahead();
+            lp::name_table::entry* v = variable(e.name);
+            if (v->owner != -2) {
+                v->owner = -2;
+                v->position = static_cast<int32_t>(out.objective.size());
+                out.objective.emplace_back(e.factor, v->id);
             } else
-                out.objective[where[id].second].first += e.factor;
+                out.objective[v->position].first += e.factor;
         }
         t.pop(e.used);
     }
@@ -471,14 +540,14 @@ lp_parse(std::string text, bxg_lp& out)
                     const lp::element e = lp::read_element(t);
                     if (!e.ok || e.used == 0)
                         return "bad_constraint";
-                    const int id = variable(e.name);
-                    if (static_cast<size_t>(id) >= where.size())
-                        where.resize(out.vars.size() + out.vars.size() / 2 + 16, { -1, 0 });
-                    if (where[id].first != next_id) {
-                        where[id] = { next_id, static_cast<int>(r.elements.size()) };
-                        r.elements.emplace_back(static_cast<int>(e.factor), id);
+                    look_ahead();
+                    lp::name_table::entry* v = variable(e.name);
+                    if (v->owner != next_id) {
+                        v->owner = next_id;
+                        v->position = static_cast<int32_t>(r.elements.size());
+                        r.elements.emplace_back(static_cast<int>(e.factor), v->id);
                     } else
-                        r.elements[where[id].second].first += static_cast<int>(e.factor);
+                        r.elements[v->position].first += static_cast<int>(e.factor);
                     t.pop(e.used);
                 }
                 const int opn = lp::read_operator(t.at(0), t.at(1), r.op);
