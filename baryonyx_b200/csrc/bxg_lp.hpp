@@ -683,8 +683,8 @@ lp_parse(std::string text, bxg_lp& out)
 std::string
 lp_merge(bxg_lp& p, int pre_order)
 {
-    if (pre_order != 0 && pre_order != 1)
-        return "pre_constraint_order other than none / memory is outside this engine";
+    if (pre_order < 0 || pre_order > 11)
+        return "unknown pre_constraint_order";
     int coef = 0;
     bool inequality = false;
     for (const lp::row& r : p.rows) {
@@ -722,9 +722,15 @@ lp_merge(bxg_lp& p, int pre_order)
     };
     std::unordered_map<const std::vector<std::pair<int, int>>*, size_t, key_hash, key_eq> seen;
     std::vector<merged> out;
-    // equal first, then less, then greater (the order of the three passes
-    // decides which row of a merged group keeps its id)
-    for (int pass : { 0, -1, 1 }) {
+    // The order of the three passes decides which row of a merged group keeps
+    // its id: equal, less, greater for none / memory / p1-p4
+    // (make_unsorted_merged_constraints), the order named by the parameter for
+    // the six type orders (make_ordered_merged_constraints, :177-210).
+    static const int pass_order[12][3] = { { 0, -1, 1 }, { 0, -1, 1 }, { -1, 1, 0 }, { -1, 0, 1 },
+                                           { 1, -1, 0 }, { 1, 0, -1 }, { 0, -1, 1 }, { 0, 1, -1 },
+                                           { 0, -1, 1 }, { 0, -1, 1 }, { 0, -1, 1 }, { 0, -1, 1 } };
+    const bool by_type = pre_order >= 2 && pre_order <= 7, special = pre_order >= 8;
+    for (int pass : pass_order[pre_order]) {
         for (const lp::row& r : p.rows) {
             if (r.op != pass)
                 continue;
@@ -747,13 +753,45 @@ lp_merge(bxg_lp& p, int pre_order)
                 m.min = std::max(m.min, r.value);
         }
     }
-    std::sort(out.begin(), out.end(), [](const merged& a, const merged& b) { return a.id < b.id; });
+    if (!by_type) // the type orders keep the rows as the passes met them
+        std::sort(out.begin(), out.end(), [](const merged& a, const merged& b) { return a.id < b.id; });
+
+    // p1-p4, make_special_merged_constraints (:219-285): rows by the smallest
+    // cost / degree ratio of their variables (p1 descending, the others
+    // ascending), elements by descending ratio.  std::sort with ties: same
+    // library, same sequence of comparisons, same permutation as the reference.
+    std::vector<double> ratio;
+    if (special) {
+        std::vector<int> degree(p.vars.size(), 0);
+        for (const merged& m : out)
+            for (const auto& e : *m.elements)
+                ++degree[e.second];
+        ratio.assign(p.vars.size(), 0.0);
+        for (const auto& o : p.objective)
+            ratio[o.second] = o.first / static_cast<double>(degree[o.second]);
+        std::vector<std::pair<int, double>> row_ratio(out.size());
+        for (size_t i = 0; i != out.size(); ++i) {
+            const auto& el = *out[i].elements;
+            row_ratio[i] = { static_cast<int>(i), ratio[el[0].second] };
+            for (size_t j = 1; j != el.size(); ++j)
+                row_ratio[i].second = std::min(row_ratio[i].second, ratio[el[j].second]);
+        }
+        if (pre_order == 8)
+            std::sort(row_ratio.begin(), row_ratio.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+        else
+            std::sort(row_ratio.begin(), row_ratio.end(), [](const auto& a, const auto& b) { return a.second < b.second; });
+        for (size_t i = 0; i != out.size(); ++i)
+            out[i].id = row_ratio[i].first;
+        std::sort(out.begin(), out.end(), [](const merged& a, const merged& b) { return a.id < b.id; });
+    }
 
     p.row_ptr.assign(1, 0);
     p.col.clear(), p.factor.clear(), p.cmin.clear(), p.cmax.clear();
     for (const merged& m : out) {
         std::vector<std::pair<int, int>> el(*m.elements);
-        if (pre_order == 1) // improve_memory_usage: elements by variable index
+        if (special)
+            std::sort(el.begin(), el.end(), [&ratio](const auto& a, const auto& b) { return ratio[a.second] > ratio[b.second]; });
+        else if (pre_order >= 1) // improve_memory_usage: elements by variable index
             std::sort(el.begin(), el.end(), [](const auto& a, const auto& b) { return a.second < b.second; });
         for (const auto& e : el) {
             p.factor.push_back(e.first);

@@ -307,9 +307,11 @@ uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
  * (lib/src/merged-constraint.cpp:52-175,297-343).  Same dialect and the same
  * conventions: variables numbered by first appearance, coefficients and
  * right-hand sides truncated to int, rows over the same elements merged into
- * one [min, max] row, rows in file order.  pre_order: 0 = none, 1 = memory
- * (elements of a row sorted by variable), the reference's other orders are
- * BXG_E_INVALID; so are quadratic objectives.  Host code, no device needed.
+ * one [min, max] row.  pre_order = the reference's pre_constraint_order
+ * (core:296-330): 0 none (rows in file order), 1 memory (+ elements of a row
+ * sorted by variable), 2-7 rows grouped by type in the named order, 8-11
+ * p1-p4 (rows and elements by cost / degree ratio).  Quadratic objectives are
+ * BXG_E_INVALID.  Host code, no device needed.
  * On a malformed file bxg_last_error() carries the reference's
  * file_format_error_tag name. */
 typedef struct bxg_lp bxg_lp;

@@ -30,7 +30,7 @@ def parse_with_reference(path: str, pre_order: int) -> dict:
 
 if __name__ == "__main__":
     for lp in sorted(glob.glob(os.path.join(HERE, "lp", "*.lp"))):
-        doc = {f"pre_order_{o}": parse_with_reference(lp, o) for o in (0, 1)}
+        doc = {f"pre_order_{o}": parse_with_reference(lp, o) for o in range(12)}
         with open(lp[:-3] + ".json", "w") as f:
             json.dump(doc, f, separators=(",", ":"))
         d = doc["pre_order_0"]

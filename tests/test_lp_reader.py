@@ -43,7 +43,7 @@ def test_golden_lp_fixtures_present():
 
 
 @pytest.mark.parametrize("lp", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-@pytest.mark.parametrize("pre_order", [0, 1])
+@pytest.mark.parametrize("pre_order", list(range(12)))
 def test_reader_matches_reference_golden(lp, pre_order):
     want = json.load(open(lp[:-3] + ".json"))[f"pre_order_{pre_order}"]
     same_parse(capi.read_lp(path=lp, pre_order=pre_order), want, lp)
@@ -117,9 +117,10 @@ def test_missing_file():
     assert "file_not_found" in str(e.value)
 
 
-def test_unsupported_pre_order():
-    with pytest.raises(capi.BxgError):
-        capi.read_lp(text="minimize\n x\nst\n c: x <= 1\nend\n", pre_order=2)
+def test_unknown_pre_order():
+    for bad in (-1, 12):
+        with pytest.raises(capi.BxgError):
+            capi.read_lp(text="minimize\n x\nst\n c: x <= 1\nend\n", pre_order=bad)
 
 
 @pytest.mark.parametrize("make", [
@@ -153,12 +154,13 @@ REF_LPS = sorted(glob.glob(os.path.join(REF_DIR, "**", "*.lp"), recursive=True))
 
 @pytest.mark.skipif(not (REF_LPS and po.ref_available()), reason="needs /root/reference and oracle/_ref (build container)")
 def test_every_reference_fixture_parses_like_the_reference():
-    """All LP files the reference ships (lib/test/*.lp and the rest), both
-    supported constraint orders, against the compiled reference's parser."""
+    """All LP files the reference ships (lib/test/*.lp and the rest), all twelve
+    pre_constraint_order values, against the compiled reference's parser and
+    make_merged_constraints."""
     assert len(REF_LPS) >= 50
     compared = 0
     for lp in REF_LPS:
-        for pre_order in (0, 1):
+        for pre_order in range(12):
             p = po.default_params()
             p.pre_order = pre_order
             try:
@@ -172,7 +174,7 @@ def test_every_reference_fixture_parses_like_the_reference():
             r.close()
             same_parse(capi.read_lp(path=lp, pre_order=pre_order), want, (lp, pre_order))
             compared += 1
-    assert compared >= 100
+    assert compared >= 600
 
 
 @pytest.mark.gpu
