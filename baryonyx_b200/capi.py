@@ -77,7 +77,7 @@ EXPORTS = [
     "bxg_population_mutation", "bxg_population_try_update", "bxg_population_try_advance",
     "bxg_population_score", "bxg_optimize_round", "bxg_bit_array_hash",
     "bxg_lp_read", "bxg_lp_parse", "bxg_lp_destroy", "bxg_lp_info", "bxg_lp_rows", "bxg_lp_objective",
-    "bxg_lp_variable",
+    "bxg_lp_variable", "bxg_lp_variables", "bxg_lp_names",
 ]
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -465,11 +465,16 @@ def read_lp(path: str | None = None, text: str | None = None, pre_order: int = 0
         check(L.bxg_lp_rows(h, row_ptr, col, fac, cmin, cmax))
         ov, of = np.zeros(max(nobj.value, 1), np.int32), np.zeros(max(nobj.value, 1), np.float64)
         check(L.bxg_lp_objective(h, ov, of))
-        names, bounds = [], []
-        for i in range(n):
-            lo, hi, ty = C.c_int(), C.c_int(), C.c_int()
-            names.append(L.bxg_lp_variable(h, i, C.byref(lo), C.byref(hi), C.byref(ty)).decode())
-            bounds.append((lo.value, hi.value, ty.value))
+        L.bxg_lp_variables.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
+        L.bxg_lp_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        lo, hi, ty = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+        check(L.bxg_lp_variables(h, lo, hi, ty))
+        need = C.c_size_t()
+        check(L.bxg_lp_names(h, None, 0, C.byref(need)))
+        raw = C.create_string_buffer(max(need.value, 1))
+        check(L.bxg_lp_names(h, raw, need.value, C.byref(need)))
+        names = raw.raw[: need.value].decode().split("\0")[:n]
+        bounds = list(zip(lo[:n].tolist(), hi[:n].tolist(), ty[:n].tolist()))
         return {"m": m, "n": n, "row_ptr": row_ptr, "col": col[:nnz], "factor": fac[:nnz], "cmin": cmin[:m],
                 "cmax": cmax[:m], "problem_type": ptype, "maximize": maximize, "obj_var": ov[: nobj.value],
                 "obj_factor": of[: nobj.value], "cost_constant": cc.value, "names": names, "bounds": bounds}

@@ -905,6 +905,39 @@ bxg_lp_variable(const bxg_lp* p, int i, int* min, int* max, int* type)
     return p->vars[i].name.c_str();
 }
 
+int
+bxg_lp_variables(const bxg_lp* p, int32_t* min, int32_t* max, int32_t* type)
+{
+    if (!p || !min || !max || !type)
+        return fail(BXG_E_INVALID, "bxg_lp_variables: bad argument");
+    for (size_t i = 0; i != p->vars.size(); ++i) {
+        min[i] = p->vars[i].min;
+        max[i] = p->vars[i].max;
+        type[i] = p->vars[i].type;
+    }
+    return BXG_OK;
+}
+
+int
+bxg_lp_names(const bxg_lp* p, char* buffer, size_t capacity, size_t* needed)
+{
+    if (!p || !needed)
+        return fail(BXG_E_INVALID, "bxg_lp_names: bad argument");
+    size_t total = 0;
+    for (const auto& v : p->vars)
+        total += v.name.size() + 1;
+    *needed = total;
+    if (!buffer)
+        return BXG_OK;
+    if (capacity < total)
+        return fail(BXG_E_INVALID, "bxg_lp_names: buffer too small");
+    for (const auto& v : p->vars) {
+        std::memcpy(buffer, v.name.c_str(), v.name.size() + 1);
+        buffer += v.name.size() + 1;
+    }
+    return BXG_OK;
+}
+
 } // extern "C"
 
 #endif

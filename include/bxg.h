@@ -327,6 +327,11 @@ int bxg_lp_rows(const bxg_lp* lp, int32_t* row_ptr, int32_t* col,
 int bxg_lp_objective(const bxg_lp* lp, int32_t* obj_var, double* obj_factor);
 /* name (owned by the handle), bounds and variable_type (0 real, 1 binary, 2 general) */
 const char* bxg_lp_variable(const bxg_lp* lp, int i, int* min, int* max, int* type);
+/* the same for all n variables at once: min / max / type[n]; the names as n
+ * NUL-terminated strings back to back (needed = their total size; a null
+ * buffer only asks for it) */
+int bxg_lp_variables(const bxg_lp* lp, int32_t* min, int32_t* max, int32_t* type);
+int bxg_lp_names(const bxg_lp* lp, char* buffer, size_t capacity, size_t* needed);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,28 @@ def test_malformed_text_is_refused_with_the_reference_tag(text, tag, reference, 
             po.RefProblem(str(f), po.default_params())
 
 
+def test_per_variable_and_bulk_queries_agree():
+    """bxg_lp_variable (one at a time) against bxg_lp_variables / bxg_lp_names."""
+    lp = os.path.join(LP_DIR, "general_bounds.lp")
+    d = capi.read_lp(path=lp)  # bulk
+    L = capi.lib()
+    h = C.c_void_p()
+    capi.check(L.bxg_lp_read(lp.encode(), 0, C.byref(h)))
+    try:
+        for i in range(d["n"]):
+            lo, hi, ty = C.c_int(), C.c_int(), C.c_int()
+            name = L.bxg_lp_variable(h, i, C.byref(lo), C.byref(hi), C.byref(ty))
+            assert name.decode() == d["names"][i]
+            assert (lo.value, hi.value, ty.value) == d["bounds"][i]
+        assert L.bxg_lp_variable(h, d["n"], None, None, None) is None
+        need = C.c_size_t()
+        small = C.create_string_buffer(2)
+        assert L.bxg_lp_names(h, small, 2, C.byref(need)) != 0  # too small: refused, nothing written
+        assert need.value == sum(len(n) + 1 for n in d["names"])
+    finally:
+        L.bxg_lp_destroy(h)
+
+
 def test_missing_file():
     with pytest.raises(capi.BxgError) as e:
         capi.read_lp(path="/nonexistent/file.lp")
