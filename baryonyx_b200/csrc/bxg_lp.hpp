@@ -17,6 +17,7 @@
 #define BXG_LP_HPP
 
 #include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <sys/mman.h>
@@ -804,6 +805,26 @@ lp_merge(bxg_lp& p, int pre_order)
     return "";
 }
 
+int
+lp_build(std::string text, int pre_order, bxg_lp** out)
+{
+    std::unique_ptr<bxg_lp> p(new (std::nothrow) bxg_lp);
+    if (!p)
+        return fail(BXG_E_MEMORY, "out of host memory");
+    std::string err;
+    try {
+        err = lp_parse(std::move(text), *p);
+        if (err.empty())
+            err = lp_merge(*p, pre_order);
+    } catch (const std::bad_alloc&) {
+        return fail(BXG_E_MEMORY, "out of host memory");
+    }
+    if (!err.empty())
+        return fail(BXG_E_INVALID, "LP text: " + err);
+    *out = p.release();
+    return BXG_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -813,16 +834,7 @@ bxg_lp_parse(const char* text, size_t length, int pre_order, bxg_lp** out)
 {
     if (!text || !out)
         return fail(BXG_E_INVALID, "bxg_lp_parse: bad argument");
-    std::unique_ptr<bxg_lp> p(new (std::nothrow) bxg_lp);
-    if (!p)
-        return fail(BXG_E_MEMORY, "out of host memory");
-    std::string err = lp_parse(std::string(text, length), *p);
-    if (err.empty())
-        err = lp_merge(*p, pre_order);
-    if (!err.empty())
-        return fail(BXG_E_INVALID, "LP text: " + err);
-    *out = p.release();
-    return BXG_OK;
+    return lp_build(std::string(text, length), pre_order, out);
 }
 
 int
@@ -830,11 +842,23 @@ bxg_lp_read(const char* path, int pre_order, bxg_lp** out)
 {
     if (!path || !out)
         return fail(BXG_E_INVALID, "bxg_lp_read: bad argument");
-    std::ifstream f(path, std::ios::binary);
+    std::FILE* f = std::fopen(path, "rb");
     if (!f)
         return fail(BXG_E_INVALID, std::string("LP text: file_not_found: ") + path);
-    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    return bxg_lp_parse(text.data(), text.size(), pre_order, out);
+    std::string text;
+    char chunk[1 << 16];
+    if (std::fseek(f, 0, SEEK_END) == 0) { // one read when the size is known
+        const long size = std::ftell(f);
+        std::rewind(f);
+        if (size > 0) {
+            text.resize(static_cast<size_t>(size));
+            text.resize(std::fread(&text[0], 1, text.size(), f));
+        }
+    }
+    for (size_t got; (got = std::fread(chunk, 1, sizeof chunk, f)) > 0;) // pipes, files that grew
+        text.append(chunk, got);
+    std::fclose(f);
+    return lp_build(std::move(text), pre_order, out);
 }
 
 void
