@@ -1,9 +1,11 @@
 """time bxg_lp_read against the compiled reference's
 make_problem + make_merged_constraints (oracle/_ref) on the same LP text.
 Host code on one core each; build container only (needs oracle/_ref).
+Test infrastructure (it runs the checker next to the product), hence under tests/;
+not collected by pytest.
 
-    python tools/lp_reader_timing.py [m n]      # rail-shaped instance, default 2000 x 200000
-    python tools/lp_reader_timing.py m n --no-reference   # C5 scale: the reference's quadratic
+    python tests/lp_reader_timing.py [m n]      # rail-shaped instance, default 2000 x 200000
+    python tests/lp_reader_timing.py m n --no-reference   # C5 scale: the reference's quadratic
                                                 # look-ups make it impractical there; the parse is
                                                 # checked against the instance the file was written from
 """
