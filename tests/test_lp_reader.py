@@ -234,3 +234,85 @@ def test_parsed_file_solves_like_the_oracle(lp):
     bt.close()
     op.close()
     pb.close()
+
+
+def _random_lp(rng) -> str:
+    """Well-formed LP text with the dialect's variety: labels or none, decimal
+    and exponent coefficients, repeated variables, the operator spellings,
+    the bound forms, binary / general sections."""
+    n = int(rng.integers(2, 9))
+    names = [rng.choice(["x", "y_", "var.", "Q"]) + str(int(rng.integers(0, 50))) + rng.choice(["", "a", "_z"])
+             for _ in range(n)]
+    names = list(dict.fromkeys(names))
+
+    def coef(first):
+        v = rng.choice([1, 1, 1, 2, 3, 2.5, 10, 0.5, 7])
+        sign = rng.choice(["+", "-"])
+        txt = {2.5: "2.5", 0.5: "0.5", 10: rng.choice(["10", "1e1"])}.get(v, str(int(v)))
+        if v == 1 and rng.random() < 0.6:
+            txt = ""
+        lead = "" if (first and sign == "+" and rng.random() < 0.5) else sign + rng.choice([" ", ""])
+        return lead + txt + (" " if txt and rng.random() < 0.7 else "")
+
+    def expr(k):
+        picks = [names[int(i)] for i in rng.integers(0, len(names), size=k)]
+        return " ".join(coef(i == 0) + v for i, v in enumerate(picks))
+
+    out = [rng.choice(["minimize", "maximize", "Minimize", "MAX", "min"])]
+    if rng.random() < 0.8:
+        label = "obj: " if rng.random() < 0.5 else ""
+        const = rng.choice(["", " + 4", " - 2.5"])
+        out.append(" " + label + expr(int(rng.integers(1, 6))) + const)
+    out.append(rng.choice(["subject to", "st", "s.t.", "Subject To"]))
+    for k in range(int(rng.integers(1, 7))):
+        label = f"c{k}: " if rng.random() < 0.6 else ""
+        op = rng.choice(["<=", ">=", "=", "=<", "=>", "<", ">"])
+        rhs = rng.choice(["0", "1", "2", "3", "-1", "2.7", "+2"])
+        out.append(" " + label + expr(int(rng.integers(1, 5))) + " " + op + " " + rhs)
+    kind = rng.choice(["binary", "bounds", "general", "none"])
+    if kind == "bounds":
+        out.append("bounds")
+        for v in names:
+            form = rng.choice(["up", "both", "skip"])
+            if form == "up":
+                out.append(f" {v} <= {int(rng.integers(1, 5))}")
+            elif form == "both":
+                out.append(f" {int(rng.integers(0, 2))} <= {v} <= {int(rng.integers(2, 6))}")
+    elif kind == "binary":
+        out.append(rng.choice(["binary", "binaries", "bin"]))
+        out.append(" " + " ".join(names))
+    elif kind == "general":
+        out.append("bounds")
+        out.extend(f" {v} <= 3" for v in names)
+        out.append(rng.choice(["general", "generals", "gen"]))
+        out.append(" " + " ".join(names))
+    out.append(rng.choice(["end", "End"]))
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_DIR) and po.ref_available()), reason="needs oracle/_ref (build container)")
+def test_random_texts_parse_like_the_reference(tmp_path):
+    """Differential run: 300 generated LP texts, a random constraint order
+    each, the engine's reader against the compiled reference's."""
+    rng = np.random.default_rng(20261018)
+    compared = refused = 0
+    for case in range(300):
+        text = _random_lp(rng)
+        pre_order = int(rng.integers(0, 12))
+        f = tmp_path / f"r{case}.lp"
+        f.write_text(text)
+        p = po.default_params()
+        p.pre_order = pre_order
+        try:
+            r = po.RefProblem(str(f), p)
+        except RuntimeError:
+            with pytest.raises(capi.BxgError):
+                capi.read_lp(text=text, pre_order=pre_order)
+            refused += 1
+            continue
+        want = r.instance()
+        want["names"], want["bounds"] = r.variables()
+        r.close()
+        same_parse(capi.read_lp(text=text, pre_order=pre_order), want, (case, pre_order, text))
+        compared += 1
+    assert compared >= 150, (compared, refused)
