@@ -3049,3 +3049,307 @@ ox_pop_try_advance(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x, int remaining,
             return;
     pop_replace(pop, c, x, pop_results(pop->pb, x), hash, loop, remaining);
 }
+
+/* ======================================================================== */
+/* optimize_functor::operator() at thread = 1,                              */
+/* itm-optimizer-common.hpp:596-752 (set up like optimize_problem, :795-826) */
+/* ======================================================================== */
+
+/* generate_seed, itm-common.hpp:1457-1484, continuing the master engine */
+static void
+ox_generate_seed_from_state(uint32_t* master, unsigned count, uint64_t* out)
+{
+    if (count == 0)
+        return;
+    out[0] = ox_uniform_u64(0, UINT64_MAX, master);
+    for (unsigned i = 1; i != count; ++i) {
+        out[i] = ox_uniform_u64(0, UINT64_MAX, master);
+        unsigned j = i - 1;
+        while (j > 0) {
+            if (out[j] == out[i]) {
+                out[j] = ox_uniform_u64(0, UINT64_MAX, master);
+                j = i;
+            }
+            --j;
+        }
+    }
+}
+
+struct ox_opt_trace
+{
+    int rounds; /* snapshots taken (restarts + 1) */
+    int m, nnz, blocks, size;
+    uint64_t* x;    /* [rounds][blocks] */
+    uint32_t* rng;  /* [rounds] */
+    double* kappa;  /* [rounds] */
+    double* pi;     /* [rounds][m] */
+    double* P;      /* [rounds][nnz] */
+    uint64_t* mx;   /* [rounds][size][blocks] */
+    double* mvalue; /* [rounds][size] */
+    int* mremaining;
+    uint64_t* mhash;
+    int64_t* mloop;
+    int sweeps, sweep_cap;
+    int* sweep_round;
+    int* sweep_push;
+    int* sweep_len;
+    double* sweep_kappa;
+    int cur_round;
+};
+
+static void
+trace_sweep(struct ox_opt_trace* t, const ox_run* r, int push, double kappa)
+{
+    if (t->sweeps == t->sweep_cap) {
+        t->sweep_cap = t->sweep_cap ? 2 * t->sweep_cap : 1024;
+        t->sweep_round = (int*)realloc(t->sweep_round, sizeof(int) * (size_t)t->sweep_cap);
+        t->sweep_push = (int*)realloc(t->sweep_push, sizeof(int) * (size_t)t->sweep_cap);
+        t->sweep_len = (int*)realloc(t->sweep_len, sizeof(int) * (size_t)t->sweep_cap);
+        t->sweep_kappa = (double*)realloc(t->sweep_kappa, sizeof(double) * (size_t)t->sweep_cap);
+    }
+    const int pairs =
+      r->order == OX_ORDER_INFEASIBILITY_DECR || r->order == OX_ORDER_INFEASIBILITY_INCR;
+    t->sweep_round[t->sweeps] = t->cur_round;
+    t->sweep_push[t->sweeps] = push;
+    t->sweep_len[t->sweeps] = pairs ? r->m_order_len : r->oR_len;
+    t->sweep_kappa[t->sweeps] = kappa;
+    t->sweeps++;
+}
+
+static void
+trace_snapshot(struct ox_opt_trace* t, int slot, const ox_run* r, const struct ox_pop* pop,
+               double kappa)
+{
+    const ox_problem* pb = r->pb;
+    memcpy(t->x + (size_t)slot * t->blocks, r->x, sizeof(uint64_t) * (size_t)t->blocks);
+    t->rng[slot] = r->rng;
+    t->kappa[slot] = kappa;
+    memcpy(t->pi + (size_t)slot * t->m, r->pi, sizeof(double) * (size_t)t->m);
+    memcpy(t->P + (size_t)slot * t->nnz, r->P, sizeof(double) * (size_t)t->nnz);
+    for (int i = 0; i != t->size; ++i) {
+        const ox_member* mb = &pop->data[pop->indices[i]];
+        const size_t o = (size_t)slot * t->size + i;
+        memcpy(t->mx + o * t->blocks, mb->x, sizeof(uint64_t) * (size_t)t->blocks);
+        t->mvalue[o] = mb->value;
+        t->mremaining[o] = mb->remaining;
+        t->mhash[o] = mb->hash;
+        t->mloop[o] = mb->loop;
+    }
+    (void)pb;
+}
+
+/* One sweep of the traced worker: the engine is the worker's (local_context::rng
+ * is the engine the Solver holds by reference). */
+static int
+opt_sweep(ox_run* r, struct ox_opt_trace* t, double kappa, int push, double amp)
+{
+    trace_sweep(t, r, push, kappa);
+    return order_run(r, kappa, r->delta, r->theta, push, amp);
+}
+
+static void
+opt_try_update(ox_run* r, struct ox_pop* pop, struct ox_pop_ctx* c, int64_t loop)
+{
+    c->rng = r->rng;
+    ox_pop_try_update(pop, c, r->x, results(r), loop);
+    r->rng = c->rng;
+}
+
+ox_opt_trace*
+ox_opt_trace_run(ox_problem* pb, const ox_params* p, uint32_t seed, int rounds)
+{
+    /* optimize_problem: random_engine rng(seed); best_solution_recorder(rng, ...);
+     * seeds = generate_seed(rng, thread); functor(ctx, 0, seeds[0]) */
+    uint32_t master = 0;
+    struct ox_pop* pop = ox_pop_create(pb, p, seed, 1, &master);
+    uint64_t wseed = 0;
+    ox_generate_seed_from_state(&master, 1, &wseed);
+    struct ox_pop_ctx* c = ox_pop_ctx_create(pop, 0, wseed);
+
+    /* the functor's Solver, x = 0, compute_order(order, n) */
+    ox_params q = *p;
+    q.init_policy_random = 0.0;
+    ox_run* r = ox_run_begin(pb, &q, 1);
+    if (!r) {
+        ox_pop_ctx_destroy(c);
+        ox_pop_destroy(pop);
+        return NULL;
+    }
+    r->p = *p;
+    memset(r->x, 0, sizeof(uint64_t) * (size_t)r->x_blocks);
+    r->rng = c->rng;
+    {
+        const int n = pb->n;
+        r->oR_len = n;
+        r->m_order_len = n;
+        for (int i = 0; i != n; ++i) {
+            r->oR[i] = 0;
+            r->m_order[i].first = 0;
+            r->m_order[i].second = 0;
+        }
+    }
+
+    struct ox_opt_trace* t = (struct ox_opt_trace*)calloc(1, sizeof(struct ox_opt_trace));
+    t->rounds = rounds + 1;
+    t->m = pb->m;
+    t->nnz = pb->nnz;
+    t->blocks = r->x_blocks;
+    t->size = pop->size;
+    t->x = (uint64_t*)calloc((size_t)t->rounds * t->blocks, sizeof(uint64_t));
+    t->rng = (uint32_t*)calloc((size_t)t->rounds, sizeof(uint32_t));
+    t->kappa = (double*)calloc((size_t)t->rounds, sizeof(double));
+    t->pi = (double*)calloc((size_t)t->rounds * t->m, sizeof(double));
+    t->P = (double*)calloc((size_t)t->rounds * t->nnz + 1, sizeof(double));
+    t->mx = (uint64_t*)calloc((size_t)t->rounds * t->size * t->blocks, sizeof(uint64_t));
+    t->mvalue = (double*)calloc((size_t)t->rounds * t->size, sizeof(double));
+    t->mremaining = (int*)calloc((size_t)t->rounds * t->size, sizeof(int));
+    t->mhash = (uint64_t*)calloc((size_t)t->rounds * t->size, sizeof(uint64_t));
+    t->mloop = (int64_t*)calloc((size_t)t->rounds * t->size, sizeof(int64_t));
+
+    const double kappa_step = p->kappa_step, kappa_max = p->kappa_max, alpha = p->alpha;
+    const long w_limit = (long)p->w;
+
+    for (int round = 0; round <= rounds; ++round) {
+        t->cur_round = round;
+        c->rng = r->rng;
+        const double kappa_start = ox_pop_reinit(pop, c, p->kappa_min, p->kappa_max, r->x);
+        r->rng = c->rng;
+        double kappa = kappa_start;
+        order_init(r);
+        trace_snapshot(t, round, r, pop, kappa);
+        if (round == rounds)
+            break;
+
+        int best_remaining = INT_MAX;
+        for (int64_t i = 0; i != p->limit; ++i) {
+            const int remaining = opt_sweep(r, t, kappa, 0, 0.0);
+            if (remaining == 0) {
+                opt_try_update(r, pop, c, i);
+                best_remaining = 0;
+                break;
+            } else if (remaining < best_remaining)
+                best_remaining = remaining;
+
+            if (i > w_limit)
+                kappa += kappa_step * pow((double)remaining / (double)pb->m, alpha);
+            if (kappa > kappa_max)
+                break;
+        }
+
+        if (best_remaining > 0) {
+            c->rng = r->rng;
+            ox_pop_try_advance(pop, c, r->x, best_remaining, p->limit);
+            r->rng = c->rng;
+            continue;
+        }
+
+        for (int push = 0; push < p->pushes_limit; ++push) {
+            int remaining =
+              opt_sweep(r, t, p->pushing_k_factor, 1, p->pushing_objective_amplifier);
+            if (remaining == 0)
+                opt_try_update(r, pop, c, -(int64_t)push * p->pushing_iteration_limit - 1);
+
+            kappa = kappa_start;
+            for (int iter = 0; iter < p->pushing_iteration_limit; ++iter) {
+                remaining = opt_sweep(r, t, kappa, 0, 0.0);
+                if (remaining == 0) {
+                    opt_try_update(r, pop, c,
+                                   -(int64_t)push * p->pushing_iteration_limit - iter - 1);
+                    break;
+                }
+                if (iter > p->w)
+                    kappa += kappa_step * pow((double)remaining / (double)pb->m, alpha);
+                if (kappa > kappa_max)
+                    break;
+            }
+        }
+    }
+
+    ox_run_end(r);
+    ox_pop_ctx_destroy(c);
+    ox_pop_destroy(pop);
+    return t;
+}
+
+void
+ox_opt_trace_free(ox_opt_trace* t)
+{
+    if (!t)
+        return;
+    free(t->x);
+    free(t->rng);
+    free(t->kappa);
+    free(t->pi);
+    free(t->P);
+    free(t->mx);
+    free(t->mvalue);
+    free(t->mremaining);
+    free(t->mhash);
+    free(t->mloop);
+    free(t->sweep_round);
+    free(t->sweep_push);
+    free(t->sweep_len);
+    free(t->sweep_kappa);
+    free(t);
+}
+
+int
+ox_opt_trace_rounds(ox_opt_trace* t)
+{
+    return t->rounds;
+}
+
+int
+ox_opt_trace_round(ox_opt_trace* t, int r, uint64_t* x_words, uint32_t* rng_state, double* kappa,
+                   double* pi, double* P)
+{
+    if (r < 0 || r >= t->rounds)
+        return -1;
+    if (x_words)
+        memcpy(x_words, t->x + (size_t)r * t->blocks, sizeof(uint64_t) * (size_t)t->blocks);
+    if (rng_state)
+        *rng_state = t->rng[r];
+    if (kappa)
+        *kappa = t->kappa[r];
+    if (pi)
+        memcpy(pi, t->pi + (size_t)r * t->m, sizeof(double) * (size_t)t->m);
+    if (P)
+        memcpy(P, t->P + (size_t)r * t->nnz, sizeof(double) * (size_t)t->nnz);
+    return 0;
+}
+
+int
+ox_opt_trace_member(ox_opt_trace* t, int r, int i, uint64_t* x_words, double* value,
+                    int* remaining, uint64_t* hash, int64_t* loop)
+{
+    if (r < 0 || r >= t->rounds || i < 0 || i >= t->size)
+        return -1;
+    const size_t o = (size_t)r * t->size + i;
+    if (x_words)
+        memcpy(x_words, t->mx + o * t->blocks, sizeof(uint64_t) * (size_t)t->blocks);
+    if (value)
+        *value = t->mvalue[o];
+    if (remaining)
+        *remaining = t->mremaining[o];
+    if (hash)
+        *hash = t->mhash[o];
+    if (loop)
+        *loop = t->mloop[o];
+    return 0;
+}
+
+int
+ox_opt_trace_sweeps(ox_opt_trace* t)
+{
+    return t->sweeps;
+}
+
+int
+ox_opt_trace_sweep_log(ox_opt_trace* t, int* round, int* push, double* kappa, int* len)
+{
+    memcpy(round, t->sweep_round, sizeof(int) * (size_t)t->sweeps);
+    memcpy(push, t->sweep_push, sizeof(int) * (size_t)t->sweeps);
+    memcpy(kappa, t->sweep_kappa, sizeof(double) * (size_t)t->sweeps);
+    memcpy(len, t->sweep_len, sizeof(int) * (size_t)t->sweeps);
+    return 0;
+}

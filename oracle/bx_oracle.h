@@ -201,6 +201,21 @@ void ox_pop_try_advance(ox_pop* pop, ox_pop_ctx* c, const uint64_t* x_words,
                         int remaining, int64_t loop);
 uint64_t ox_bit_array_hash(int n, const uint64_t* x_words);
 
+/* optimize_functor::operator() at thread = 1 (itm-optimizer-common.hpp:596-752),
+ * set up like optimize_problem (:795-826) from ctx.parameters.seed = seed and run
+ * for `rounds` restarts.  Same layout as bxref_opt_trace (ref_harness/bxref.h):
+ * snapshot r is the state at the first sweep of restart r. */
+typedef struct ox_opt_trace ox_opt_trace;
+ox_opt_trace* ox_opt_trace_run(ox_problem* pb, const ox_params* p, uint32_t seed, int rounds);
+void ox_opt_trace_free(ox_opt_trace* t);
+int ox_opt_trace_rounds(ox_opt_trace* t);
+int ox_opt_trace_round(ox_opt_trace* t, int r, uint64_t* x_words, uint32_t* rng_state,
+                       double* kappa, double* pi, double* P);
+int ox_opt_trace_member(ox_opt_trace* t, int r, int i, uint64_t* x_words, double* value,
+                        int* remaining, uint64_t* hash, int64_t* loop);
+int ox_opt_trace_sweeps(ox_opt_trace* t);
+int ox_opt_trace_sweep_log(ox_opt_trace* t, int* round, int* push, double* kappa, int* len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,16 @@ def oracle():
         C.c_void_p, C.POINTER(Params), C.c_uint32, _i8p, C.POINTER(C.c_double),
         C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
     ]
+    lib.ox_opt_trace_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_int]
+    lib.ox_opt_trace_run.restype = C.c_void_p
+    lib.ox_opt_trace_free.argtypes = [C.c_void_p]
+    lib.ox_opt_trace_rounds.argtypes = [C.c_void_p]
+    lib.ox_opt_trace_round.argtypes = [C.c_void_p, C.c_int, _u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_double),
+                                       _f64p, _f64p]
+    lib.ox_opt_trace_member.argtypes = [C.c_void_p, C.c_int, C.c_int, _u64p, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+    lib.ox_opt_trace_sweeps.argtypes = [C.c_void_p]
+    lib.ox_opt_trace_sweep_log.argtypes = [C.c_void_p, _i32p, _i32p, _f64p, _i32p]
     lib.ox_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
     lib.ox_exhaustive_solve.argtypes = [C.c_int, _i32p, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
     _oracle = lib
@@ -238,6 +248,18 @@ class OracleProblem:
 
     def run(self, params: Params, seed: int) -> "OracleRun":
         return OracleRun(self, params, seed)
+
+    def optimize_trace(self, params: Params, seed: int, rounds: int):
+        """optimize_functor at thread = 1 for `rounds` restarts (ox_opt_trace_run);
+        `params` clamped.  Same arrays as RefProblem.optimize_trace."""
+        t = self.lib.ox_opt_trace_run(self.h, C.byref(params), seed, rounds)
+        if not t:
+            raise RuntimeError("ox_opt_trace_run failed")
+        try:
+            return read_opt_trace(self.lib, "ox_opt_trace", t, self.m, self.n, self.nnz,
+                                  params.init_population_size)
+        finally:
+            self.lib.ox_opt_trace_free(t)
 
     def solve(self, params: Params, seed: int):
         x = np.zeros(self.n, np.int8)
@@ -336,6 +358,16 @@ def ref(fast: bool = False):
     lib.bxref_optimize.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_double, _i8p, C.POINTER(C.c_double),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_double)]
+    lib.bxref_opt_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+    lib.bxref_opt_trace.restype = C.c_void_p
+    lib.bxref_opt_trace_free.argtypes = [C.c_void_p]
+    lib.bxref_opt_trace_rounds.argtypes = [C.c_void_p]
+    lib.bxref_opt_trace_round.argtypes = [C.c_void_p, C.c_int, _u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_double),
+                                          _f64p, _f64p]
+    lib.bxref_opt_trace_member.argtypes = [C.c_void_p, C.c_int, C.c_int, _u64p, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+    lib.bxref_opt_trace_sweeps.argtypes = [C.c_void_p]
+    lib.bxref_opt_trace_sweep_log.argtypes = [C.c_void_p, _i32p, _i32p, _f64p, _i32p]
     lib.bxref_std_sort.argtypes = [_f64p, _i32p, C.c_int, C.c_int]
     lib.bxref_std_sort_pairs.argtypes = [_i32p, _i32p, C.c_int, C.c_int]
     lib.bxref_std_shuffle.argtypes = [_i32p, C.c_int, C.POINTER(C.c_uint32)]
@@ -352,6 +384,35 @@ def ref(fast: bool = False):
     lib.bxref_exhaustive_solve.argtypes = [C.c_int, _i32p, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
     _ref[fast] = lib
     return lib
+
+
+def read_opt_trace(lib, prefix, t, m, n, nnz, size):
+    """Arrays of an optimizer trace (reference harness or oracle, same layout)."""
+    f = lambda name: getattr(lib, prefix + "_" + name)
+    words = n // 64 + 1
+    R = f("rounds")(t)
+    out = {"x": np.zeros((R, words), np.uint64), "rng": np.zeros(R, np.uint32), "kappa": np.zeros(R),
+           "pi": np.zeros((R, m)), "P": np.zeros((R, nnz)),
+           "pop_x": np.zeros((R, size, words), np.uint64), "pop_value": np.zeros((R, size)),
+           "pop_remaining": np.zeros((R, size), np.int32), "pop_hash": np.zeros((R, size), np.uint64),
+           "pop_loop": np.zeros((R, size), np.int64)}
+    for r in range(R):
+        rng, kappa = C.c_uint32(), C.c_double()
+        f("round")(t, r, out["x"][r], C.byref(rng), C.byref(kappa), out["pi"][r], out["P"][r])
+        out["rng"][r], out["kappa"][r] = rng.value, kappa.value
+        for i in range(size):
+            v, rem, h, lp = C.c_double(), C.c_int(), C.c_uint64(), C.c_int64()
+            f("member")(t, r, i, out["pop_x"][r, i], C.byref(v), C.byref(rem), C.byref(h), C.byref(lp))
+            out["pop_value"][r, i], out["pop_remaining"][r, i] = v.value, rem.value
+            out["pop_hash"][r, i], out["pop_loop"][r, i] = h.value, lp.value
+    S = f("sweeps")(t)
+    out["sweep_round"] = np.zeros(S, np.int32)
+    out["sweep_push"] = np.zeros(S, np.int32)
+    out["sweep_kappa"] = np.zeros(S)
+    out["sweep_len"] = np.zeros(S, np.int32)
+    if S:
+        f("sweep_log")(t, out["sweep_round"], out["sweep_push"], out["sweep_kappa"], out["sweep_len"])
+    return out
 
 
 class RefProblem:
@@ -436,6 +497,16 @@ class RefProblem:
                                      C.byref(upd), C.byref(swp), C.byref(sec))
         return {"status": st, "x": x, "value": value.value, "remaining": rem.value,
                 "updates": upd.value, "sweeps": swp.value, "seconds": sec.value}
+
+    def optimize_trace(self, seed: int, rounds: int, population_size: int):
+        """The reference's optimize_functor at thread = 1, stopped after `rounds`
+        restarts (bxref_opt_trace): per-restart snapshots (x, engine, kappa, pi, P,
+        population in sorted order) and the sweep log."""
+        t = self.lib.bxref_opt_trace(self.h, seed, rounds)
+        try:
+            return read_opt_trace(self.lib, "bxref_opt_trace", t, self.m, self.n, self.nnz, population_size)
+        finally:
+            self.lib.bxref_opt_trace_free(t)
 
     def close(self):
         if self.h:

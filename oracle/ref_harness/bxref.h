@@ -112,6 +112,24 @@ int bxref_optimize(void* h, uint32_t seed, int threads, double time_limit,
                    int8_t* x, double* value, int* remaining, int64_t* updates,
                    int64_t* sweeps, double* seconds);
 
+/* Trace of the optimizer at thread = 1: the reference's own optimize_functor
+ * (itm-optimizer-common.hpp:596-752) on the calling thread, set up as
+ * optimize_problem does (:795-826), stopped after `rounds` restarts.  Snapshot
+ * r (0 <= r <= rounds) is taken at the first sweep of restart r (0-based), i.e.
+ * after reinit + compute_order::init: snapshot `rounds` holds everything the
+ * first `rounds` restarts did.  Members are in sorted order. */
+void* bxref_opt_trace(void* h, uint32_t seed, int rounds);
+void bxref_opt_trace_free(void* t);
+int bxref_opt_trace_rounds(void* t); /* snapshots taken */
+int bxref_opt_trace_round(void* t, int r, uint64_t* x_words, uint32_t* rng_state,
+                          double* kappa, double* pi, double* P);
+int bxref_opt_trace_member(void* t, int r, int i, uint64_t* x_words, double* value,
+                           int* remaining, uint64_t* hash, int64_t* loop);
+/* one entry per sweep of the traced restarts: restart, push flag, kappa, length
+ * of the order list */
+int bxref_opt_trace_sweeps(void* t);
+int bxref_opt_trace_sweep_log(void* t, int* round, int* push, double* kappa, int* len);
+
 /* libstdc++ primitives the path depends on (pins for the C restatement). */
 void bxref_std_sort(double* value, int* id, int n, int descending);
 void bxref_std_sort_pairs(int* first, int* second, int n, int descending);

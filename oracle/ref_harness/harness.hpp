@@ -11,6 +11,7 @@
 #include "problem.hpp"
 
 #include <atomic>
+#include <functional>
 #include <memory>
 #include <sstream>
 #include <vector>
@@ -65,12 +66,46 @@ struct solve_out
     double seconds = 0;
 };
 
+// trace of the optimizer at thread = 1 (filled by harness_solver.hpp's tracing<>)
+struct trace_member
+{
+    std::vector<uint64_t> x;
+    double value;
+    int remaining;
+    uint64_t hash;
+    int64_t loop;
+};
+
+struct trace_round
+{
+    std::vector<uint64_t> x;
+    uint32_t rng;
+    double kappa;
+    std::vector<double> pi, P;
+    std::vector<trace_member> members;
+};
+
+struct trace_data
+{
+    std::vector<trace_round> rounds; // [rounds + 1]: state at the first sweep of each restart
+    std::vector<int> sweep_round, sweep_push, sweep_len;
+    std::vector<double> sweep_kappa;
+    // live part
+    const long int* call_number = nullptr;
+    long int last_call = 0;
+    int max_rounds = 0;
+    std::atomic_bool* stop = nullptr;
+    std::function<void(trace_round&)> population;
+};
+
+
 // Per-solver factories, defined in harness_<solver>.cpp.
 #define BXREF_DECLARE(tag)                                                   \
     run_base* make_run_##tag(handle& h, uint32_t seed);                       \
     void solve_##tag(handle& h, uint32_t seed, solve_out& out);               \
     void optimize_##tag(                                                      \
-      handle& h, uint32_t seed, int threads, double tl, solve_out& out);
+      handle& h, uint32_t seed, int threads, double tl, solve_out& out);     \
+    void trace_##tag(handle& h, uint32_t seed, int rounds, trace_data& t);
 
 BXREF_DECLARE(eq01)
 BXREF_DECLARE(ineq01)

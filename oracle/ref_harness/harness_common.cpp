@@ -491,6 +491,94 @@ bxref_optimize(void* hv,
     return out.status;
 }
 
+void*
+bxref_opt_trace(void* hv, uint32_t seed, int rounds)
+{
+    auto* h = static_cast<bxref::handle*>(hv);
+    auto t = std::make_unique<bxref::trace_data>();
+#define CALL(tag) bxref::trace_##tag(*h, seed, rounds, *t)
+    BXREF_DISPATCH(h, CALL)
+#undef CALL
+    t->call_number = nullptr;
+    t->stop = nullptr;
+    t->population = nullptr;
+    return t.release();
+}
+
+void
+bxref_opt_trace_free(void* t)
+{
+    delete static_cast<bxref::trace_data*>(t);
+}
+
+int
+bxref_opt_trace_rounds(void* tv)
+{
+    return static_cast<int>(static_cast<bxref::trace_data*>(tv)->rounds.size());
+}
+
+int
+bxref_opt_trace_round(void* tv, int r, uint64_t* x_words, uint32_t* rng_state, double* kappa,
+                      double* pi, double* P)
+{
+    auto* t = static_cast<bxref::trace_data*>(tv);
+    if (r < 0 || r >= static_cast<int>(t->rounds.size()))
+        return -1;
+    const auto& s = t->rounds[r];
+    if (x_words)
+        std::copy(s.x.begin(), s.x.end(), x_words);
+    if (rng_state)
+        *rng_state = s.rng;
+    if (kappa)
+        *kappa = s.kappa;
+    if (pi)
+        std::copy(s.pi.begin(), s.pi.end(), pi);
+    if (P)
+        std::copy(s.P.begin(), s.P.end(), P);
+    return 0;
+}
+
+int
+bxref_opt_trace_member(void* tv, int r, int i, uint64_t* x_words, double* value, int* remaining,
+                       uint64_t* hash, int64_t* loop)
+{
+    auto* t = static_cast<bxref::trace_data*>(tv);
+    if (r < 0 || r >= static_cast<int>(t->rounds.size()))
+        return -1;
+    const auto& ms = t->rounds[r].members;
+    if (i < 0 || i >= static_cast<int>(ms.size()))
+        return -1;
+    const auto& m = ms[i];
+    if (x_words)
+        std::copy(m.x.begin(), m.x.end(), x_words);
+    if (value)
+        *value = m.value;
+    if (remaining)
+        *remaining = m.remaining;
+    if (hash)
+        *hash = m.hash;
+    if (loop)
+        *loop = m.loop;
+    return 0;
+}
+
+int
+bxref_opt_trace_sweeps(void* tv)
+{
+    return static_cast<int>(static_cast<bxref::trace_data*>(tv)->sweep_len.size());
+}
+
+int
+bxref_opt_trace_sweep_log(void* tv, int* round, int* push, double* kappa, int* len)
+{
+    auto* t = static_cast<bxref::trace_data*>(tv);
+    std::copy(t->sweep_round.begin(), t->sweep_round.end(), round);
+    std::copy(t->sweep_push.begin(), t->sweep_push.end(), push);
+    std::copy(t->sweep_kappa.begin(), t->sweep_kappa.end(), kappa);
+    std::copy(t->sweep_len.begin(), t->sweep_len.end(), len);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // libstdc++ primitives
 // ---------------------------------------------------------------------------

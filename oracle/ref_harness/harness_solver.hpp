@@ -14,6 +14,7 @@
 #include "itm-solver-common.hpp"
 
 #include <chrono>
+#include <functional>
 
 namespace bxref {
 
@@ -295,6 +296,114 @@ optimize_impl(handle& h,
     out.seconds = std::chrono::duration<double>(end - start).count();
 }
 
+
+// ---------------------------------------------------------------------------
+// Deterministic trace of the optimizer at thread = 1: the reference's own
+// optimize_functor (itm-optimizer-common.hpp:596-752) run on the calling
+// thread against its own best_solution_recorder, set up exactly like
+// optimize_problem does (:795-826: master engine -> recorder -> generate_seed
+// -> functor 0).  The Solver subclass only observes: at the first sweep of
+// every restart it snapshots x, the engine, pi, P and the population, and it
+// raises stop_task once `rounds` restarts are complete.
+// ---------------------------------------------------------------------------
+inline thread_local trace_data* tl_trace = nullptr;
+
+template<typename Base>
+struct tracing : Base
+{
+    using Base::Base;
+
+    template<typename Xtype>
+    bool observe(Xtype& x, int len, double kappa, int push)
+    {
+        trace_data* t = tl_trace;
+        if (!t)
+            return true;
+        if (*t->call_number != t->last_call) {
+            t->last_call = *t->call_number;
+            trace_round r;
+            for (int i = 0, e = x.block_size(); i != e; ++i)
+                r.x.push_back(x.block(i));
+            r.rng = rng_state_of(this->rng);
+            r.kappa = kappa;
+            r.pi.assign(this->pi.get(), this->pi.get() + this->m);
+            r.P.assign(this->P.get(), this->P.get() + this->ap.size());
+            t->population(r);
+            t->rounds.push_back(std::move(r));
+            if (t->last_call > t->max_rounds)
+                t->stop->store(true);
+        }
+        if (t->stop->load())
+            return false; // past the traced restarts: nothing more is recorded
+        t->sweep_round.push_back(static_cast<int>(t->last_call - 1));
+        t->sweep_push.push_back(push);
+        t->sweep_len.push_back(len);
+        t->sweep_kappa.push_back(kappa);
+        return true;
+    }
+
+    template<typename Xtype, typename Iterator, typename Float>
+    bool compute_update_row(Xtype& x, Iterator first, Iterator last, Float kappa, Float delta,
+                            Float theta)
+    {
+        observe(x, static_cast<int>(std::distance(first, last)), kappa, 0);
+        return Base::compute_update_row(x, first, last, kappa, delta, theta);
+    }
+
+    template<typename Xtype, typename Iterator, typename Float>
+    bool push_and_compute_update_row(Xtype& x, Iterator first, Iterator last, Float kappa,
+                                     Float delta, Float theta, Float obj_amp)
+    {
+        observe(x, static_cast<int>(std::distance(first, last)), kappa, 1);
+        return Base::push_and_compute_update_row(x, first, last, kappa, delta, theta, obj_amp);
+    }
+};
+
+template<typename Solver, typename Mode>
+void
+trace_impl(handle& h, uint32_t seed, int rounds, trace_data& t)
+{
+    using Cost = default_cost_type<double>;
+
+    context ctx(h.ctx);
+    ctx.parameters.seed = seed;
+    ctx.parameters.thread = 1;
+
+    random_engine rng(init_random_generator_seed(ctx));
+    auto cost = Cost(h.pb.objective, h.n);
+    const auto cost_constant = h.pb.objective.value;
+
+    best_solution_recorder<Cost, double, Mode> recorder(
+      rng, 1u, cost, cost_constant, h.n, h.csts, ctx.parameters.init_population_size);
+    auto seeds = generate_seed(rng, 1u);
+
+    optimize_functor<tracing<Solver>, double, Mode, Cost> functor(ctx, 0u, seeds[0]);
+    std::atomic_bool stop;
+    stop.store(false);
+
+    t.call_number = &functor.m_call_number;
+    t.last_call = 0;
+    t.max_rounds = rounds;
+    t.stop = &stop;
+    t.population = [&](trace_round& r) {
+        const int size = ctx.parameters.init_population_size;
+        r.members.resize(size);
+        for (int i = 0; i != size; ++i) {
+            const auto& m = recorder.get_best(i);
+            for (int b = 0, e = m.x.block_size(); b != e; ++b)
+                r.members[i].x.push_back(m.x.block(b));
+            r.members[i].value = m.value;
+            r.members[i].remaining = m.remaining_constraints;
+            r.members[i].hash = m.hash;
+            r.members[i].loop = m.loop;
+        }
+    };
+
+    tl_trace = &t;
+    functor(stop, recorder, h.csts, h.n, cost, cost_constant);
+    tl_trace = nullptr;
+}
+
 #define BXREF_DEFINE(tag, SOLVER)                                             \
     run_base* make_run_##tag(handle& h, uint32_t seed)                        \
     {                                                                         \
@@ -325,6 +434,16 @@ optimize_impl(handle& h,
         else                                                                  \
             optimize_impl<SOLVER<double, minimize_tag, Cost, false>,          \
                           minimize_tag>(h, seed, threads, tl, out);           \
+    }                                                                         \
+    void trace_##tag(handle& h, uint32_t seed, int rounds, trace_data& t)     \
+    {                                                                         \
+        using Cost = default_cost_type<double>;                               \
+        if (h.pb.type == objective_function_type::maximize)                   \
+            trace_impl<SOLVER<double, maximize_tag, Cost, false>,             \
+                       maximize_tag>(h, seed, rounds, t);                     \
+        else                                                                  \
+            trace_impl<SOLVER<double, minimize_tag, Cost, false>,             \
+                       minimize_tag>(h, seed, rounds, t);                     \
     }
 
 } // namespace bxref
