@@ -72,10 +72,11 @@ EXPORTS = [
     "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_launches",
     "bxg_batch_words32", "bxg_batch_begin_device", "bxg_batch_set_lane_params",
     "bxg_population_create", "bxg_population_destroy", "bxg_population_size",
-    "bxg_population_master_state", "bxg_population_member", "bxg_population_worker_seed",
+    "bxg_population_master_state", "bxg_population_generate_seeds", "bxg_population_member", "bxg_population_worker_seed",
     "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
     "bxg_population_mutation", "bxg_population_try_update", "bxg_population_try_advance",
-    "bxg_population_score", "bxg_optimize_round", "bxg_bit_array_hash",
+    "bxg_population_score", "bxg_optimize_round", "bxg_optimize_reinit", "bxg_optimize_run",
+    "bxg_bit_array_hash",
     "bxg_lp_read", "bxg_lp_parse", "bxg_lp_destroy", "bxg_lp_info", "bxg_lp_rows", "bxg_lp_objective",
     "bxg_lp_variable", "bxg_lp_variables", "bxg_lp_names",
 ]
@@ -338,6 +339,7 @@ def _bind_population(L):
     L.bxg_population_destroy.argtypes = [C.c_void_p]
     L.bxg_population_size.argtypes = [C.c_void_p]
     L.bxg_population_master_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.bxg_population_generate_seeds.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.bxg_population_member.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double),
                                         C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
     L.bxg_population_worker_seed.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
@@ -350,6 +352,8 @@ def _bind_population(L):
     L.bxg_population_try_advance.argtypes = [C.c_void_p, C.c_int, _u64p, C.c_int, C.c_int64]
     L.bxg_population_score.argtypes = [C.c_void_p, _u64p, C.c_int, _i32p, _f64p]
     L.bxg_optimize_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bxg_optimize_reinit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.bxg_optimize_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bxg_bit_array_hash.argtypes = [C.c_int, _u64p]
     L.bxg_bit_array_hash.restype = C.c_uint64
     L._pop_bound = True
@@ -382,6 +386,12 @@ class Population:
 
     def members(self):
         return [self.member(i) for i in range(self.size())]
+
+    def generate_seeds(self, count: int) -> np.ndarray:
+        """generate_seed on the master engine (after the constructor)."""
+        out = np.zeros(count, np.uint64)
+        check(lib().bxg_population_generate_seeds(self.h, count, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def ctx(self, worker: int, seed: int):
         check(lib().bxg_population_worker_seed(self.h, worker, seed))
@@ -425,6 +435,20 @@ class Population:
         val = np.zeros(batch.n_lanes, np.float64)
         rem = np.zeros(batch.n_lanes, np.int32)
         check(lib().bxg_optimize_round(batch.h, self.h, int(first_round), _ptr(st), _ptr(val), _ptr(rem)))
+        return {"status": st, "value": val, "remaining": rem}
+
+    def optimize_reinit(self, batch: "Batch", first_round: bool):
+        """First half of a round (parity tap): reinit of every lane; returns the kappas."""
+        k = np.zeros(batch.n_lanes, np.float64)
+        check(lib().bxg_optimize_reinit(batch.h, self.h, int(first_round), _ptr(k)))
+        return k
+
+    def optimize_run(self, batch: "Batch"):
+        """Second half of a round: the lanes' runs with the offers to the population."""
+        st = np.zeros(batch.n_lanes, np.int32)
+        val = np.zeros(batch.n_lanes, np.float64)
+        rem = np.zeros(batch.n_lanes, np.int32)
+        check(lib().bxg_optimize_run(batch.h, self.h, _ptr(st), _ptr(val), _ptr(rem)))
         return {"status": st, "value": val, "remaining": rem}
 
     def hash(self, x: np.ndarray) -> int:

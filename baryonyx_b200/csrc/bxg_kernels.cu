@@ -67,6 +67,10 @@ struct Shared
     int order_state;
     int tmp_i;
     int slow; // the current row goes to the single-thread path
+    int stop;    // the deadline has passed (time_limit / stop_task)
+    int x_dirty; // a bit of x changed since x_value / x_hash were computed
+    double x_value;            // default_cost_type::results of x
+    unsigned long long x_hash; // bit_array_hash of x
     double d;
     double kk; // kappa / (1 - kappa) of the current sweep
     double tmp_d;
@@ -121,6 +125,7 @@ struct Lane
     int tab_dirty; // the table must be cleared before its next use
     unsigned long long updates;
     unsigned long long sweeps;
+    unsigned long long offers, inserts;
     double alg_bytes;
     // updates by selection path: 0 exact single thread, 1 CTA sort, 2 two
     // smallest, 3 boundary by sign; and the cycles thread 0 spent in each
@@ -590,6 +595,7 @@ affect_element(Lane& L, int r0, int id, const int4 info, double pv, bool in, dou
     const bool was = (x[j >> 5] & bit) != 0;
     if (was != set) {
         atomicXor(&x[j >> 5], bit);
+        the_shared()->x_dirty = 1;
         const int sgn = set ? 1 : -1;
         // the rows of the column, eight independent loads at a time (the CTA
         // waits for the few threads whose bit flips: one memory round trip
@@ -1273,8 +1279,10 @@ update_row_z(int k, double kappa, int push, double obj_amp)
             const int j = info.w;
             const uint32_t bit = 1u << (j & 31);
             const bool flips = ((x[j >> 5] & bit) != 0) != set;
-            if (flips)
+            if (flips) {
                 atomicXor(&x[j >> 5], bit);
+                sh->x_dirty = 1;
+            }
 
             // local_compute_reduced_cost, :295-306, with the new pi_k and P
             double sum = 0.0;
@@ -1458,6 +1466,12 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     if (tid == 0) {
         L.sweeps += 1;
         L.sh->kk = __ddiv_rn(kappa, __dsub_rn(1.0, kappa));
+        if (L.pr->deadline_ns) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now > L.pr->deadline_ns)
+                L.sh->stop = 1;
+        }
     }
     __syncthreads();
 
@@ -1695,8 +1709,12 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         sh->order_state = ctl->order_state;
         sh->pi_changed = 0;
         sh->remaining = ctl->remaining;
+        sh->stop = 0;
+        sh->x_dirty = 1;
         L.updates = 0;
         L.sweeps = 0;
+        L.offers = 0;
+        L.inserts = 0;
         L.alg_bytes = 0.0;
         for (int i = 0; i < 4; ++i) {
             L.n_path[i] = 0;
@@ -1745,6 +1763,8 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
         L.ctl->remaining = L.sh->remaining;
         L.ctl->updates += L.updates;
         L.ctl->sweeps += L.sweeps;
+        L.ctl->offers += L.offers;
+        L.ctl->inserts += L.inserts;
         L.ctl->alg_bytes += L.alg_bytes;
         for (int i = 0; i < 4; ++i) {
             L.ctl->n_path[i] += L.n_path[i];
@@ -1928,6 +1948,223 @@ store_best(Lane& L, const DevBatch& b, int lane_id, bool by_value, double value,
         best_remaining = remaining;
 }
 
+// ---------------------------------------------------------------------------
+// optimizer: offers to the population and one call of a worker's loop body
+// ---------------------------------------------------------------------------
+
+// storage::sort's comparator, itm-optimizer-common.hpp:427-441
+struct PopLess
+{
+    const int* rem;
+    const double* val;
+    bool maximize;
+    __device__ bool operator()(const int& a, const int& b) const
+    {
+        const int ra = rem[a], rb = rem[b];
+        if (ra < rb)
+            return true;
+        if (ra == rb)
+            return maximize ? val[a] > val[b] : val[a] < val[b];
+        return false;
+    }
+};
+
+template<typename T>
+__device__ __forceinline__ T
+ld_vol(const T* p)
+{
+    return *reinterpret_cast<const volatile T*>(p);
+}
+
+// @region pop_offer
+// best_solution_recorder::try_update (solution) / try_advance (:556-584) with
+// the lane's current x: bit_array_hash + objective (kept while x does not
+// change), can_be_inserted (:302-326), and when the population takes it
+// storage::insert (:228-300): the victim drawn from the lane's engine --
+// the same engine the sweeps draw from, as in the reference, where
+// local_context::rng is the engine the Solver holds -- replace_result, sort.
+// All threads call; the population is locked for the duration.
+__device__ __noinline__ void
+pop_offer(Lane& L, const DevBatch& b, bool solution, int remaining, long long loop)
+{
+    const DevProblem& pb = *L.pb;
+    const DevPop& pop = b.pop;
+    Shared* const sh = L.sh;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    if (sh->x_dirty) { // uniform: written before the barrier that ended the sweep
+        const double v = objective(L);
+        if (tid < 32) {
+            // bit_array_hash, bit-array.hpp:410-423: a sequential fold over the
+            // n/64+1 blocks; the warp fetches 32 blocks at a time
+            const int blocks = pb.xw32 >> 1;
+            unsigned long long h = 0;
+            for (int base = 0; base < blocks; base += 32) {
+                const int i = base + tid;
+                unsigned long long w = 0;
+                if (i < blocks)
+                    w = (unsigned long long)L.x[2 * i] | ((unsigned long long)L.x[2 * i + 1] << 32);
+                const int cnt = min(32, blocks - base);
+                for (int j = 0; j < cnt; ++j) {
+                    const unsigned long long bj = __shfl_sync(0xffffffffu, w, j);
+                    h ^= bj + 0x9e3779b9ull + (h << 6) + (h >> 2);
+                }
+            }
+            if (tid == 0) {
+                sh->x_hash = h;
+                sh->x_value = v;
+                sh->x_dirty = 0;
+            }
+        }
+        __syncthreads();
+    }
+    const double value = sh->x_value;
+    const unsigned long long hash = sh->x_hash;
+
+    if (tid == 0) {
+        L.offers += 1;
+        while (atomicCAS(pop.lock, 0, 1) != 0)
+            __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+
+    int found = 0;
+    for (int i = tid; i < pop.size; i += T) {
+        const int r = ld_vol(pop.remaining + i);
+        const unsigned long long h = ld_vol(pop.hash + i);
+        if (solution)
+            found |= (r == 0 && ld_vol(pop.value + i) == value && h == hash);
+        else
+            found |= (r == remaining && h == hash);
+    }
+    found = __syncthreads_or(found);
+
+    if (!found) {
+        if (tid == 0) {
+            // choose_a_bad_solution: uniform_int_distribution<int>(size / 5, size - 1)
+            uint32_t rng = sh->rng;
+            const int pos = pop.victim_lo + (int)uniform_below(rng, (uint32_t)(pop.victim_hi - pop.victim_lo));
+            sh->rng = rng;
+            const int id = ld_vol(pop.order + pos);
+            sh->tmp_i = id;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            // replace_result, :127-144 (a solution keeps the value it was offered with;
+            // an advance stores costs.results(x))
+            pop.value[id] = value;
+            pop.remaining[id] = solution ? 0 : remaining;
+            pop.hash[id] = hash;
+            pop.loop[id] = loop;
+            pop.duration[id] = (double)(now - pop.t0_ns) * 1e-9;
+            L.inserts += 1;
+        }
+        __syncthreads();
+        uint32_t* dst = pop.x + (size_t)sh->tmp_i * pb.xw32;
+        for (int w = tid; w < pb.xw32; w += T)
+            dst[w] = L.x[w];
+
+        // sort(): keys staged in the lane's staging buffer (idle between sweeps)
+        double* s_val = L.stage;
+        int* s_rem = reinterpret_cast<int*>(s_val + pop.size);
+        int* s_ord = s_rem + pop.size;
+        for (int i = tid; i < pop.size; i += T) {
+            s_val[i] = ld_vol(pop.value + i);
+            s_rem[i] = ld_vol(pop.remaining + i);
+            s_ord[i] = ld_vol(pop.order + i);
+        }
+        __syncthreads();
+        if (tid == 0)
+            seq_std_sort(Plain<int>{ s_ord }, pop.size, PopLess{ s_rem, s_val, pb.maximize != 0 });
+        __syncthreads();
+        for (int i = tid; i < pop.size; i += T)
+            pop.order[i] = s_ord[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+        atomicExch(pop.lock, 0);
+}
+
+// @region k_optimize
+// One call of the loop body of optimize_functor::operator()
+// (itm-optimizer-common.hpp:658-750) for one lane = one worker: compute.init,
+// the sweeps with the kappa schedule from the kappa reinit returned, then the
+// push phase; every solution met is offered to the population where the
+// reference offers it, the run's last x with the best count otherwise.  x was
+// prepared by k_reinit; the Solver state (P, pi) carries over from the
+// previous call.  The deadline plays stop_task.
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k_optimize(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams pr,
+           const __grid_constant__ DevBatch b, SmemPlan plan)
+{
+    const int lane_id = blockIdx.x;
+    Lists ls;
+    Lane& L = lane_open(ls, pb, pr, b, lane_id, plan, g_smem);
+    Shared* const sh = L.sh;
+    order_init(L, ls);
+
+    const long w_limit = (long)pr.w;
+    const double kappa_start = b.plan[lane_id].kappa;
+    const double kappa_step = L.kappa_step;
+    double kappa = kappa_start;
+    int best_remaining = INT_MAX;
+    int is_solution = 0;
+    double last_value = 0.0;
+
+    for (long long i = 0; !sh->stop && i != pr.limit; ++i) {
+        const int remaining = order_run(L, ls, kappa, 0, 0.0);
+        if (remaining == 0) {
+            pop_offer(L, b, true, 0, i);
+            best_remaining = 0;
+            is_solution = 1;
+            break;
+        }
+        best_remaining = remaining < best_remaining ? remaining : best_remaining;
+        if (i > w_limit)
+            kappa = __dadd_rn(kappa, __dmul_rn(kappa_step, pr.powtab[remaining]));
+        if (kappa > pr.kappa_max)
+            break;
+    }
+
+    if (best_remaining > 0) {
+        pop_offer(L, b, false, best_remaining, pr.limit);
+    } else {
+        for (int push = 0; !sh->stop && push < pr.pushes_limit; ++push) {
+            int remaining =
+              order_run(L, ls, pr.pushing_k_factor, 1, pr.pushing_objective_amplifier);
+            if (remaining == 0)
+                pop_offer(L, b, true, 0, -(long long)push * pr.pushing_iteration_limit - 1);
+
+            kappa = kappa_start;
+            for (int iter = 0; !sh->stop && iter < pr.pushing_iteration_limit; ++iter) {
+                remaining = order_run(L, ls, kappa, 0, 0.0);
+                if (remaining == 0) {
+                    pop_offer(L, b, true, 0,
+                              -(long long)push * pr.pushing_iteration_limit - iter - 1);
+                    break;
+                }
+                if ((double)iter > pr.w)
+                    kappa = __dadd_rn(kappa, __dmul_rn(kappa_step, pr.powtab[remaining]));
+                if (kappa > pr.kappa_max)
+                    break;
+            }
+        }
+    }
+    if (is_solution)
+        last_value = sh->x_dirty ? 0.0 : sh->x_value;
+
+    if (threadIdx.x == 0) {
+        L.ctl->status = sh->stop ? 3 : (is_solution ? 0 : 5);
+        L.ctl->best_remaining = best_remaining;
+        L.ctl->best_has_x = is_solution;
+        L.ctl->best_loop = 0;
+        L.ctl->best_value = last_value;
+    }
+    lane_close(L, ls, pb, b, lane_id, plan);
+}
+
 // Whole solver_functor::operator() loop (itm-solver-common.hpp:135-225) for
 // one lane; the wall-clock time limit is handled by the host (limit sweeps).
 template<int MAXT, int MINB>
@@ -1982,9 +2219,15 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
             status = 4; // kappa_max_reached
             break;
         }
+        if (L.sh->stop) { // is_timelimit_reached(), itm-solver-common.hpp:162-165
+            status = 3;
+            break;
+        }
     }
 
     if (!start_push) {
+        // (the reference overwrites kappa_max_reached / time_limit_reached here
+        // too: itm-solver-common.hpp:169-170)
         status = 5; // limit_reached
     } else {
         for (int push = 0; push < pr.pushes_limit; ++push) {
@@ -1998,6 +2241,8 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
                            -(long long)push * pr.pushing_iteration_limit - 1,
                            m_best_remaining, m_best_value, m_best_loop, m_best_has_x);
             }
+            if (L.sh->stop)
+                break;
 
             if (optimizer)
                 kappa = kappa_start;
@@ -2016,6 +2261,8 @@ k_solve(const __grid_constant__ DevProblem pb, const __grid_constant__ DevParams
                     kappa = __dadd_rn(kappa, __dmul_rn(kappa_step, pr.powtab[remaining]));
 
                 if (kappa > pr.kappa_max)
+                    break;
+                if (L.sh->stop)
                     break;
             }
         }
@@ -2253,6 +2500,14 @@ BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBat
 {
     SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan, optimizer);
+}
+
+void
+BXG_FAM_FN(launch_optimize)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
+                const LaunchCfg& cfg, cudaStream_t s)
+{
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    BXG_LAUNCH_HOT(k_optimize, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
 void

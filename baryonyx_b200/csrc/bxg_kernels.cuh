@@ -105,6 +105,10 @@ struct DevParams
     int pushes_limit, pushing_iteration_limit;
     int order; // constraint_order as configured (may be ORDER_CYCLE)
     double tail_value;
+    // time_limit (itm-solver-common.hpp:228-232, stop_task of the optimizer,
+    // itm-optimizer-common.hpp:857): value of %globaltimer after which a lane
+    // stops at its next sweep boundary; 0 = no limit
+    unsigned long long deadline_ns;
     const double* cost;   // [n] normalised costs
     const double* powtab; // [m+1] pow(k/m, alpha), computed by glibc on the host
 };
@@ -124,12 +128,51 @@ struct LaneCtl
     long long best_loop;
     double best_value;
     double objective;
+    // optimizer rounds: solutions / advances offered to the population and how
+    // many of them it took (try_update / try_advance)
+    unsigned long long offers;
+    unsigned long long inserts;
     unsigned long long updates;
     unsigned long long sweeps;
     double alg_bytes;
     unsigned long long n_path[4];   // updates by selection path (see Lane)
     unsigned long long cyc_path[4]; // cycles of thread 0 inside them
     unsigned long long cyc_phase[4]; // ... by phase: gather, sums, ties, affect
+};
+
+// The optimizer's population on the device: best_solution_recorder / storage
+// (itm-optimizer-common.hpp:93-594).  Shared by the lanes of a batch (its
+// workers); an insert holds `lock`, like the reference's writers hold
+// m_indices_mutex.
+struct DevPop
+{
+    int size;                 // init_population_size
+    int victim_lo, victim_hi; // bad_solution_choose's range (:83-84)
+    uint32_t* x;              // [size][xw32] members' vectors (m_data[i].x)
+    double* value;            // [size]
+    int* remaining;           // [size]
+    unsigned long long* hash; // [size]
+    long long* loop;          // [size]
+    double* duration;         // [size] seconds on the device clock since the population was built
+    int* order;               // [size] m_indices
+    int* lock;
+    const uint32_t* bastert;  // [xw32] m_bastert
+    unsigned long long t0_ns;
+};
+
+// What best_solution_recorder::reinit (:528-554) decided for one lane: the
+// scalar draws (normal distributions: glibc's log) are made on the host, the
+// work over the n variables runs on the device (k_reinit).
+struct ReinitPlan
+{
+    double kappa;     // kappa the restart begins with
+    double var_p;     // mutation: probability to touch a variable
+    double val_p;     // mutation: probability of the value 1
+    uint32_t rng;     // engine state when the device takes over (start of the mutation loop)
+    int mode;         // 0 keep x, 1 crossover(first, second), 2 member `first` := bastert, 3 := random
+    int first;        // member id
+    int second;       // member id, -1 = bastert, -2 = the lane's random vector
+    int mutate;       // the per-variable mutation loop runs
 };
 
 // Per-batch lane storage (struct of arrays over lanes).
@@ -155,6 +198,11 @@ struct DevBatch
     // (Z) items / node stack / subvector pool of the sub-solvers
     unsigned char* z_scratch; // [lanes][z_bytes]
     size_t z_bytes;
+    // optimizer rounds (bxg_optimize_round)
+    DevPop pop;
+    const ReinitPlan* plan;            // [lanes]
+    const unsigned long long* masks;   // [lanes][xw32 / 2] crossover_dist draws of a crossover
+    const unsigned long long* aux;     // [lanes][xw32 / 2] init_with_random vector of a crossover
 };
 
 struct LaunchCfg
@@ -186,7 +234,9 @@ size_t z_scratch_bytes(int max_zrow);
     void launch_solve_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,         \
                            const LaunchCfg& cfg, cudaStream_t s, int optimizer);                 \
     void launch_objective_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,     \
-                               const LaunchCfg& cfg, cudaStream_t s);
+                               const LaunchCfg& cfg, cudaStream_t s);                            \
+    void launch_optimize_f##F(const DevProblem& pb, const DevParams& pr, const DevBatch& b,      \
+                              const LaunchCfg& cfg, cudaStream_t s);
 BXG_DECLARE_FAMILY(0)
 BXG_DECLARE_FAMILY(1)
 BXG_DECLARE_FAMILY(2)
@@ -237,6 +287,15 @@ launch_objective(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
     BXG_BY_FAMILY(pb, launch_objective, pb, pr, b, cfg, s);
+}
+
+// One call of optimize_functor::operator()'s loop body on every lane, after
+// launch_reinit.
+inline void
+launch_optimize(const DevProblem& pb, const DevParams& pr, const DevBatch& b, const LaunchCfg& cfg,
+                cudaStream_t s)
+{
+    BXG_BY_FAMILY(pb, launch_optimize, pb, pr, b, cfg, s);
 }
 
 #undef BXG_BY_FAMILY

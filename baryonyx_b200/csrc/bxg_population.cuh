@@ -13,6 +13,8 @@
 #ifndef BXG_POPULATION_CUH
 #define BXG_POPULATION_CUH
 
+#include "bxg_device.cuh"
+
 namespace {
 
 // remaining constraints and objective of `count` vectors; one CTA per vector.
@@ -78,6 +80,204 @@ k_score_vectors(const __grid_constant__ DevProblem pb, const int* __restrict__ c
     }
 }
 
+
+// @region k_reinit
+// best_solution_recorder::reinit's work over the variables
+// (itm-optimizer-common.hpp:359-371,494-526) for every lane of a batch, from
+// the plan the host drew (ReinitPlan): the crossover blocks
+// x = ((x1 ^ x2) & mask) ^ x1 and the mutation loop.
+//
+// The mutation loop draws one Bernoulli(var_p) per variable and, after a hit,
+// one Bernoulli(val_p) -- two engine steps each -- so where a variable's draws
+// sit in the stream depends on the hits before it.  Seen as a sequence of
+// PAIRS of engine steps it is a two-state automaton: pair q is a "value" pair
+// iff pair q-1 was a "test" pair that hit.  Every thread takes kMutC
+// consecutive pairs (LCG jump-ahead to its first), works out what its chunk
+// does to either incoming state, and two scans over the CTA (the state maps,
+// then the number of test pairs = variables) give every chunk its incoming
+// state and its first variable: the whole stream is consumed in parallel and
+// lands exactly where the sequential loop leaves it.
+constexpr int kMutC = 16;
+
+__device__ __forceinline__ unsigned
+map_compose(unsigned g, unsigned f) // first g, then f; a map is bit0 = f(0), bit1 = f(1)
+{
+    return ((f >> (g & 1u)) & 1u) | (((f >> ((g >> 1) & 1u)) & 1u) << 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_reinit(const __grid_constant__ DevProblem pb, const __grid_constant__ DevBatch b)
+{
+    const int lane_id = blockIdx.x;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    const ReinitPlan pl = b.plan[lane_id];
+    const int blocks = pb.xw32 >> 1;
+    uint32_t* const x = b.x + (size_t)lane_id * pb.xw32;
+
+    if (pl.mode == 1) {
+        // storage::crossover(ctx, x, first, second), :359-371
+        unsigned long long* x64 = reinterpret_cast<unsigned long long*>(x);
+        const unsigned long long* x1 =
+          reinterpret_cast<const unsigned long long*>(b.pop.x + (size_t)pl.first * pb.xw32);
+        const unsigned long long* x2 =
+          pl.second >= 0
+            ? reinterpret_cast<const unsigned long long*>(b.pop.x + (size_t)pl.second * pb.xw32)
+            : (pl.second == -1 ? reinterpret_cast<const unsigned long long*>(b.pop.bastert)
+                               : b.aux + (size_t)lane_id * blocks);
+        const unsigned long long* mask = b.masks + (size_t)lane_id * blocks;
+        for (int i = tid; i < blocks; i += T) {
+            const unsigned long long a = x1[i], c = x2[i];
+            x64[i] = ((a ^ c) & mask[i]) ^ a;
+        }
+    }
+    __syncthreads();
+
+    uint32_t final_rng = pl.rng;
+    if (pl.mutate) {
+        __shared__ unsigned s_map[32];
+        __shared__ int s_cnt[32];
+        __shared__ long long s_end;
+        if (tid == 0)
+            s_end = 0;
+        const int n = pb.n;
+        const double var_p = pl.var_p, val_p = pl.val_p;
+        long long q_base = 0;
+        int i_base = 0;
+        unsigned carry = 0; // the first pair of the tile is a value pair
+        while (i_base < n) {
+            const long long q0 = q_base + (long long)tid * kMutC;
+            uint32_t st = lcg_mul(pl.rng, lcg_pow(2ull * (unsigned long long)q0));
+            unsigned A = 0, V = 0; // pair j of the chunk: u < var_p, u < val_p (one pair past the chunk too)
+#pragma unroll
+            for (int j = 0; j <= kMutC; ++j) {
+                const uint32_t g1 = lcg_next(st);
+                const uint32_t g2 = lcg_next(st);
+                const double u = canonical_from(g1, g2);
+                A |= (unsigned)(u < var_p) << j;
+                V |= (unsigned)(u < val_p) << j;
+            }
+            // what the chunk does to either incoming state, and its test pairs
+            unsigned o[2];
+            int tests[2];
+#pragma unroll
+            for (int in = 0; in != 2; ++in) {
+                unsigned sv = in;
+                int t = 0;
+#pragma unroll
+                for (int j = 0; j != kMutC; ++j) {
+                    if (sv)
+                        sv = 0;
+                    else {
+                        ++t;
+                        sv = (A >> j) & 1u;
+                    }
+                }
+                o[in] = sv;
+                tests[in] = t;
+            }
+            unsigned f = o[0] | (o[1] << 1);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned g = __shfl_up_sync(0xffffffffu, f, d);
+                if (ln >= d)
+                    f = map_compose(g, f);
+            }
+            if (ln == 31)
+                s_map[wp] = f;
+            __syncthreads();
+            unsigned before = 2u; // identity
+            for (int w = 0; w < wp; ++w)
+                before = map_compose(before, s_map[w]);
+            unsigned total = before;
+            for (int w = wp; w < nw; ++w)
+                total = map_compose(total, s_map[w]);
+            unsigned excl = __shfl_up_sync(0xffffffffu, f, 1);
+            if (ln == 0)
+                excl = 2u;
+            excl = map_compose(before, excl);
+            const unsigned in_state = (excl >> carry) & 1u;
+            const int my_tests = tests[in_state];
+
+            int incl = my_tests;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (ln >= d)
+                    incl += v;
+            }
+            if (ln == 31)
+                s_cnt[wp] = incl;
+            __syncthreads();
+            int cnt_before = 0, cnt_total = 0;
+            for (int w = 0; w < nw; ++w) {
+                const int v = s_cnt[w];
+                if (w < wp)
+                    cnt_before += v;
+                cnt_total += v;
+            }
+            int i = i_base + cnt_before + incl - my_tests;
+
+            unsigned sv = in_state;
+#pragma unroll
+            for (int j = 0; j != kMutC; ++j) {
+                if (sv)
+                    sv = 0;
+                else {
+                    const unsigned hit = (A >> j) & 1u;
+                    if (i < n) {
+                        if (hit) {
+                            // x.set(i, value): bit_array::set(int, bool), bit-array.hpp:143-148,
+                            // leaves the value in bit 0 of a block only and clears any other bit
+                            const uint32_t bit = 1u << (i & 31);
+                            if ((i & 63) == 0 && ((V >> (j + 1)) & 1u))
+                                atomicOr(&x[i >> 5], bit);
+                            else
+                                atomicAnd(&x[i >> 5], ~bit);
+                        }
+                        if (i == n - 1)
+                            s_end = q0 + j + 1 + hit;
+                    }
+                    ++i;
+                    sv = hit;
+                }
+            }
+            carry = (total >> carry) & 1u;
+            i_base += cnt_total;
+            q_base += (long long)T * kMutC;
+            __syncthreads();
+        }
+        final_rng = lcg_mul(pl.rng, lcg_pow(2ull * (unsigned long long)s_end));
+    }
+    if (tid == 0)
+        b.ctl[lane_id].rng = final_rng;
+}
+
+// storage::crossover's other branch (:389,402): member `first` takes the bits
+// of the bastert / random vector and keeps its value and hash.  After k_reinit,
+// so that no lane reads a member while it is rewritten.
+__global__ void __launch_bounds__(256)
+k_pop_replace(const __grid_constant__ DevProblem pb, const __grid_constant__ DevBatch b)
+{
+    const ReinitPlan pl = b.plan[blockIdx.x];
+    if (pl.mode != 2 && pl.mode != 3)
+        return;
+    uint32_t* dst = b.pop.x + (size_t)pl.first * pb.xw32;
+    const uint32_t* src = pl.mode == 2
+                            ? b.pop.bastert
+                            : reinterpret_cast<const uint32_t*>(b.aux + (size_t)blockIdx.x * (pb.xw32 >> 1));
+    for (int w = threadIdx.x; w < pb.xw32; w += blockDim.x)
+        dst[w] = src[w];
+}
+
+__global__ void
+k_globaltimer(unsigned long long* out)
+{
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    *out = now;
+}
+
 using engine_t = std::default_random_engine;
 
 uint32_t
@@ -134,6 +334,190 @@ struct bxg_population
     DevBuf<int> d_cmin, d_cmax, d_remaining;
     DevBuf<unsigned long long> d_x;
     DevBuf<double> d_value;
+
+    // The population as the lanes see it during bxg_optimize_round (DevPop).
+    // The host vectors above and the device copy are brought in line on demand:
+    // host_newer after the constructor or a host-side operation of this API,
+    // device_newer after a round.
+    DevBuf<uint32_t> d_px, d_bastert;
+    DevBuf<double> d_pvalue, d_pduration;
+    DevBuf<int> d_premaining, d_porder, d_plock;
+    DevBuf<unsigned long long> d_phash;
+    DevBuf<long long> d_ploop;
+    DevBuf<ReinitPlan> d_plan;
+    DevBuf<unsigned long long> d_masks, d_aux;
+    std::vector<ReinitPlan> plans;
+    bool host_newer = true, device_newer = false, reinit_done = false;
+    unsigned long long t0_ns = 0;
+    int64_t rounds = 0;
+
+    DevPop dev_view() const
+    {
+        DevPop v{};
+        v.size = size;
+        v.victim_lo = p.init_population_size / 5;
+        v.victim_hi = p.init_population_size - 1;
+        v.x = d_px.p;
+        v.value = d_pvalue.p;
+        v.remaining = d_premaining.p;
+        v.hash = d_phash.p;
+        v.loop = d_ploop.p;
+        v.duration = d_pduration.p;
+        v.order = d_porder.p;
+        v.lock = d_plock.p;
+        v.bastert = d_bastert.p;
+        v.t0_ns = t0_ns;
+        return v;
+    }
+
+    int to_device(cudaStream_t st)
+    {
+        const size_t w32 = static_cast<size_t>(words) * 2;
+        if (!d_px.p) {
+            CUDA_TRY(d_px.alloc(static_cast<size_t>(size) * w32));
+            CUDA_TRY(d_bastert.alloc(w32));
+            CUDA_TRY(d_pvalue.alloc(size));
+            CUDA_TRY(d_pduration.alloc(size));
+            CUDA_TRY(d_premaining.alloc(size));
+            CUDA_TRY(d_porder.alloc(size));
+            CUDA_TRY(d_plock.alloc(1));
+            CUDA_TRY(d_phash.alloc(size));
+            CUDA_TRY(d_ploop.alloc(size));
+            CUDA_TRY(cudaMemset(d_plock.p, 0, sizeof(int)));
+            CUDA_TRY(cudaMemset(d_pduration.p, 0, sizeof(double) * size));
+            CUDA_TRY(cudaMemcpy(d_bastert.p, bastert.data(), sizeof(uint64_t) * words,
+                                cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaStreamSynchronize(nullptr));
+        }
+        std::vector<uint64_t> flat(static_cast<size_t>(size) * words);
+        std::vector<double> value(size);
+        std::vector<int> remaining(size);
+        std::vector<unsigned long long> hash(size);
+        std::vector<long long> loop(size);
+        for (int i = 0; i != size; ++i) {
+            std::copy(data[i].x.begin(), data[i].x.end(), flat.begin() + static_cast<size_t>(i) * words);
+            value[i] = data[i].value;
+            remaining[i] = data[i].remaining;
+            hash[i] = data[i].hash;
+            loop[i] = data[i].loop;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_px.p, flat.data(), sizeof(uint64_t) * flat.size(),
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_pvalue.p, value.data(), sizeof(double) * size, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_premaining.p, remaining.data(), sizeof(int) * size,
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_phash.p, hash.data(), sizeof(unsigned long long) * size,
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_ploop.p, loop.data(), sizeof(long long) * size, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_porder.p, order.data(), sizeof(int) * size, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        host_newer = false;
+        return BXG_OK;
+    }
+
+    // scores and order only (what reinit's draws and the callers' reports need)
+    int fetch_scores(cudaStream_t st)
+    {
+        std::vector<double> value(size);
+        std::vector<int> remaining(size);
+        std::vector<unsigned long long> hash(size);
+        std::vector<long long> loop(size);
+        CUDA_TRY(cudaMemcpyAsync(value.data(), d_pvalue.p, sizeof(double) * size, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(remaining.data(), d_premaining.p, sizeof(int) * size,
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hash.data(), d_phash.p, sizeof(unsigned long long) * size,
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(loop.data(), d_ploop.p, sizeof(long long) * size, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(order.data(), d_porder.p, sizeof(int) * size, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int i = 0; i != size; ++i) {
+            data[i].value = value[i];
+            data[i].remaining = remaining[i];
+            data[i].hash = hash[i];
+            data[i].loop = loop[i];
+        }
+        return BXG_OK;
+    }
+
+    // everything, the vectors included (host-side operations, parity taps)
+    int to_host()
+    {
+        if (!device_newer)
+            return BXG_OK;
+        CUDA_TRY(cudaSetDevice(pb->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        int rc = fetch_scores(nullptr);
+        if (rc != BXG_OK)
+            return rc;
+        std::vector<uint64_t> flat(static_cast<size_t>(size) * words);
+        CUDA_TRY(cudaMemcpy(flat.data(), d_px.p, sizeof(uint64_t) * flat.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i != size; ++i)
+            data[i].x.assign(flat.begin() + static_cast<size_t>(i) * words,
+                             flat.begin() + static_cast<size_t>(i + 1) * words);
+        device_newer = false;
+        return BXG_OK;
+    }
+
+    // The draws of best_solution_recorder::reinit (:528-554) that do not run
+    // over the variables: which branch, the parents, the masks, the mutation
+    // rates.  Leaves in `pl.rng` the engine state the device continues from.
+    void plan_reinit(worker& w, double kappa_min, double kappa_max, ReinitPlan& pl,
+                     unsigned long long* masks, unsigned long long* aux)
+    {
+        pl = ReinitPlan{};
+        pl.kappa = kappa_min;
+        pl.first = pl.second = 0;
+        if (w.improve < p.init_kappa_improve_stop) {
+            w.improve += p.init_kappa_improve_increase;
+            pl.kappa = kappa_min + (kappa_max - kappa_min) * w.improve;
+        } else {
+            w.improve = p.init_kappa_improve_start;
+            // storage::crossover(ctx, x), :373-421
+            auto draw_masks = [&] {
+                for (int i = 0; i != words; ++i)
+                    masks[i] = w.mask(w.rng);
+            };
+            if (w.special_parent(w.rng)) {
+                pl.first = order[pick_parent(w)];
+                std::bernoulli_distribution coin(0.5);
+                const bool use_bastert = coin(w.rng);
+                if (!use_bastert) {
+                    std::bernoulli_distribution half(0.5);
+                    std::fill(aux, aux + words, 0ull);
+                    for (int i = 0; i != pb->n; ++i)
+                        if (half(w.rng))
+                            aux[i >> 6] |= 1ull << (i & 63);
+                }
+                if (coin(w.rng)) {
+                    pl.mode = 1;
+                    pl.second = use_bastert ? -1 : -2;
+                    draw_masks();
+                } else
+                    pl.mode = use_bastert ? 2 : 3;
+            } else {
+                pl.first = order[pick_parent(w)];
+                pl.second = order[pick_parent(w)];
+                while (pl.first == pl.second)
+                    pl.second = order[pick_parent(w)];
+                pl.mode = 1;
+                draw_masks();
+            }
+        }
+        // best_solution_recorder::mutation, :494-526
+        if (!(w.mutation_value.mean() == 0.0 && w.mutation_value.stddev() == 0.0)) {
+            double rate, ones;
+            do
+                rate = w.mutation_rate(w.rng);
+            while (rate <= 0.0 || rate >= 1.0);
+            do
+                ones = w.mutation_value(w.rng);
+            while (ones < 0.0 || ones > 1.0);
+            pl.var_p = rate;
+            pl.val_p = ones;
+            pl.mutate = 1;
+        }
+        pl.rng = engine_state(w.rng);
+    }
 
     bool maximize() const { return pb->maximize != 0; }
 
@@ -488,11 +872,38 @@ bxg_population_master_state(bxg_population* pop, uint32_t* state)
 }
 
 int
+bxg_population_generate_seeds(bxg_population* pop, int count, uint64_t* seeds)
+{
+    if (!pop || count < 1 || !seeds)
+        return fail(BXG_E_INVALID, "bxg_population_generate_seeds: bad argument");
+    // generate_seed, itm-common.hpp:1457-1484, on the master engine
+    using type = engine_t::result_type;
+    std::uniform_int_distribution<type> dst(std::numeric_limits<type>::min(),
+                                            std::numeric_limits<type>::max());
+    engine_t& rng = pop->master;
+    seeds[0] = dst(rng);
+    for (int i = 1; i != count; ++i) {
+        seeds[i] = dst(rng);
+        unsigned j = static_cast<unsigned>(i) - 1;
+        while (j > 0) {
+            if (seeds[j] == seeds[i]) {
+                seeds[j] = dst(rng);
+                j = static_cast<unsigned>(i);
+            }
+            --j;
+        }
+    }
+    return BXG_OK;
+}
+
+int
 bxg_population_member(bxg_population* pop, int i, uint64_t* x_words, double* value, int* remaining,
                       uint64_t* hash, int64_t* loop)
 {
     if (!pop || i < 0 || i >= pop->size)
         return fail(BXG_E_INVALID, "bxg_population_member: bad argument");
+    if (int rc_ = pop->to_host())
+        return rc_;
     const bxg_population::member& mb = pop->data[pop->order[i]];
     if (x_words)
         std::copy(mb.x.begin(), mb.x.end(), x_words);
@@ -553,6 +964,9 @@ bxg_population_reinit(bxg_population* pop, int worker, double kappa_min, double 
                       uint64_t* x_words, double* kappa)
 {
     BXG_WORKER(pop, worker, "bxg_population_reinit");
+    if (int rc_ = pop->to_host())
+        return rc_;
+    pop->host_newer = true;
     if (!x_words || !kappa)
         return fail(BXG_E_INVALID, "bxg_population_reinit: bad argument");
     *kappa = pop->reinit(w, kappa_min, kappa_max, x_words);
@@ -563,6 +977,9 @@ int
 bxg_population_crossover(bxg_population* pop, int worker, uint64_t* x_words)
 {
     BXG_WORKER(pop, worker, "bxg_population_crossover");
+    if (int rc_ = pop->to_host())
+        return rc_;
+    pop->host_newer = true;
     pop->crossover(w, x_words);
     return BXG_OK;
 }
@@ -571,6 +988,9 @@ int
 bxg_population_mutation(bxg_population* pop, int worker, uint64_t* x_words)
 {
     BXG_WORKER(pop, worker, "bxg_population_mutation");
+    if (int rc_ = pop->to_host())
+        return rc_;
+    pop->host_newer = true;
     pop->mutation(w, x_words);
     return BXG_OK;
 }
@@ -580,6 +1000,9 @@ bxg_population_try_update(bxg_population* pop, int worker, const uint64_t* x_wor
                           int64_t loop)
 {
     BXG_WORKER(pop, worker, "bxg_population_try_update");
+    if (int rc_ = pop->to_host())
+        return rc_;
+    pop->host_newer = true;
     pop->offer_solution(w, x_words, value, loop);
     return BXG_OK;
 }
@@ -589,6 +1012,9 @@ bxg_population_try_advance(bxg_population* pop, int worker, const uint64_t* x_wo
                            int64_t loop)
 {
     BXG_WORKER(pop, worker, "bxg_population_try_advance");
+    if (int rc_ = pop->to_host())
+        return rc_;
+    pop->host_newer = true;
     pop->offer_advance(w, x_words, remaining, loop);
     return BXG_OK;
 }
@@ -603,8 +1029,7 @@ bxg_population_score(bxg_population* pop, const uint64_t* x_words, int count, in
 }
 
 int
-bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* status,
-                   double* value, int32_t* remaining)
+bxg_optimize_reinit(bxg_batch* b, bxg_population* pop, int first_round, double* kappa)
 {
     if (!b || !pop || pop->pb != b->pb)
         return fail(BXG_E_INVALID, "bxg_optimize_round: batch and population of different problems");
@@ -614,63 +1039,141 @@ bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* 
     for (int l = 0; l != L; ++l)
         if (!pop->workers[l].seeded)
             return fail(BXG_E_INVALID, "bxg_optimize_round: seed every worker first");
+    if (pop->size > b->cfg.stage_cap || pop->size < 5)
+        return fail(BXG_E_UNSUPPORTED, "bxg_optimize_round: population size outside [5, staging buffer]");
     bxg_problem* pb = b->pb;
     CUDA_TRY(cudaSetDevice(pb->device));
     const int xw32 = pb->dev.xw32;
+    const int words = pop->words;
     const size_t xn = static_cast<size_t>(L) * xw32;
 
-    // reinit: x of the previous call (zeros at first) -> crossover / mutation
-    std::vector<uint32_t> x0(xn, 0u), rng0(L);
-    std::vector<double> kappa(L);
-    if (!first_round)
-        CUDA_TRY(cudaMemcpy(x0.data(), b->d_x.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
-    for (int l = 0; l != L; ++l) {
-        bxg_population::worker& w = pop->workers[l];
-        kappa[l] = pop->reinit(w, b->p.kappa_min, b->p.kappa_max,
-                               reinterpret_cast<uint64_t*>(x0.data() + static_cast<size_t>(l) * xw32));
-        rng0[l] = engine_state(w.rng);
+    if (pop->host_newer) {
+        int rc = pop->to_device(b->stream);
+        if (rc != BXG_OK)
+            return rc;
     }
-    if (b->d_x0.n < xn) {
-        CUDA_TRY(b->d_x0.alloc(xn));
-        CUDA_TRY(cudaStreamSynchronize(nullptr)); // the batch's stream is non-blocking
+    if (!pop->t0_ns) {
+        // the device clock the durations count from (m_start, :467-480)
+        unsigned long long* d_now = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_now), sizeof(unsigned long long), b->stream));
+        k_globaltimer<<<1, 1, 0, b->stream>>>(d_now);
+        CUDA_TRY(cudaMemcpyAsync(&pop->t0_ns, d_now, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        CUDA_TRY(cudaFreeAsync(d_now, b->stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(b->d_x0.p, x0.data(), sizeof(uint32_t) * xn, cudaMemcpyHostToDevice,
-                             b->stream));
-    CUDA_TRY(cudaMemcpyAsync(b->d_rng0.p, rng0.data(), sizeof(uint32_t) * L, cudaMemcpyHostToDevice,
-                             b->stream));
-    CUDA_TRY(cudaMemcpyAsync(b->d_kappa.p, kappa.data(), sizeof(double) * L, cudaMemcpyHostToDevice,
-                             b->stream));
-    // compute.init(slv, x); the Solver (P, pi) is only fresh in the first call
-    int rc = run_begin(b, nullptr, b->d_x0.p, b->d_rng0.p, first_round ? 1 : 0);
+
+    if (first_round) {
+        // bit_array x(variables) and a fresh Solver (:611,649): x = 0, P = pi = 0
+        std::vector<uint32_t> rng0(L);
+        for (int l = 0; l != L; ++l) {
+            rng0[l] = engine_state(pop->workers[l].rng);
+            pop->workers[l].improve = 0;
+        }
+        if (b->d_x0.n < xn) {
+            CUDA_TRY(b->d_x0.alloc(xn));
+            CUDA_TRY(cudaStreamSynchronize(nullptr)); // the batch's stream is non-blocking
+        }
+        CUDA_TRY(cudaMemsetAsync(b->d_x0.p, 0, sizeof(uint32_t) * xn, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->d_rng0.p, rng0.data(), sizeof(uint32_t) * L, cudaMemcpyHostToDevice,
+                                 b->stream));
+        int rc = run_begin(b, nullptr, b->d_x0.p, b->d_rng0.p, 1);
+        if (rc != BXG_OK)
+            return rc;
+    } else if (!b->begun)
+        return fail(BXG_E_INVALID, "bxg_optimize_round: the first call must have first_round = 1");
+
+    // the engines where the lanes left them, the order of the population
+    int rc = fetch_ctl(b);
     if (rc != BXG_OK)
         return rc;
+    if (pop->device_newer) {
+        rc = pop->fetch_scores(b->stream);
+        if (rc != BXG_OK)
+            return rc;
+    }
+
+    // reinit, host part: one plan per lane
+    pop->plans.resize(L);
+    if (pop->d_plan.n < static_cast<size_t>(L)) {
+        CUDA_TRY(pop->d_plan.alloc(L));
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+    }
+    std::vector<unsigned long long> masks(words), aux(words);
+    bool any_replace = false;
+    for (int l = 0; l != L; ++l) {
+        bxg_population::worker& w = pop->workers[l];
+        engine_set_state(w.rng, b->h_ctl[l].rng);
+        ReinitPlan& pl = pop->plans[l];
+        pop->plan_reinit(w, b->p.kappa_min, b->p.kappa_max, pl, masks.data(), aux.data());
+        if (pl.mode == 1 || pl.mode == 3) {
+            const size_t need = static_cast<size_t>(L) * words;
+            if (pop->d_masks.n < need) {
+                CUDA_TRY(pop->d_masks.alloc(need));
+                CUDA_TRY(pop->d_aux.alloc(need));
+                CUDA_TRY(cudaStreamSynchronize(nullptr));
+            }
+            // pageable source: the copy has left the host buffer when the call returns
+            if (pl.mode == 1)
+                CUDA_TRY(cudaMemcpyAsync(pop->d_masks.p + static_cast<size_t>(l) * words, masks.data(),
+                                         sizeof(unsigned long long) * words, cudaMemcpyHostToDevice,
+                                         b->stream));
+            if (pl.second == -2 || pl.mode == 3)
+                CUDA_TRY(cudaMemcpyAsync(pop->d_aux.p + static_cast<size_t>(l) * words, aux.data(),
+                                         sizeof(unsigned long long) * words, cudaMemcpyHostToDevice,
+                                         b->stream));
+        }
+        any_replace |= pl.mode == 2 || pl.mode == 3;
+    }
+    CUDA_TRY(cudaMemcpyAsync(pop->d_plan.p, pop->plans.data(), sizeof(ReinitPlan) * L,
+                             cudaMemcpyHostToDevice, b->stream));
 
     refresh_params(b);
+    b->dev.pop = pop->dev_view();
+    b->dev.plan = pop->d_plan.p;
+    b->dev.masks = pop->d_masks.p;
+    b->dev.aux = pop->d_aux.p;
+
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-    launch_solve(pb->dev, b->prm, b->dev, b->cfg, b->stream, 1);
+    // reinit, device part
+    k_reinit<<<L, 256, 0, b->stream>>>(pb->dev, b->dev);
+    b->launches += 1;
+    if (any_replace) {
+        k_pop_replace<<<L, 256, 0, b->stream>>>(pb->dev, b->dev);
+        b->launches += 1;
+        pop->device_newer = true;
+    }
+    CUDA_TRY(cudaGetLastError());
+    pop->reinit_done = true;
+    if (kappa)
+        for (int l = 0; l != L; ++l)
+            kappa[l] = pop->plans[l].kappa;
+    return BXG_OK;
+}
+
+int
+bxg_optimize_run(bxg_batch* b, bxg_population* pop, int32_t* status, double* value,
+                 int32_t* remaining)
+{
+    if (!b || !pop || pop->pb != b->pb || !pop->reinit_done)
+        return fail(BXG_E_INVALID, "bxg_optimize_run: call bxg_optimize_reinit first");
+    bxg_problem* pb = b->pb;
+    CUDA_TRY(cudaSetDevice(pb->device));
+    const int L = b->n_lanes;
+    pop->reinit_done = false;
+    launch_optimize(pb->dev, b->prm, b->dev, b->cfg, b->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
     b->launches += 1;
-    rc = fetch_ctl(b);
+    pop->device_newer = true;
+    pop->rounds += 1;
+    int rc = fetch_ctl(b);
     if (rc != BXG_OK)
         return rc;
     CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
 
-    // try_update / try_advance in lane order, each on its worker's stream
-    std::vector<uint32_t> bestx(xn);
-    CUDA_TRY(cudaMemcpy(x0.data(), b->d_x.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(bestx.data(), b->d_bestx.p, sizeof(uint32_t) * xn, cudaMemcpyDeviceToHost));
     for (int l = 0; l != L; ++l) {
         const LaneCtl& c = b->h_ctl[l];
-        bxg_population::worker& w = pop->workers[l];
-        engine_set_state(w.rng, c.rng);
-        const size_t off = static_cast<size_t>(l) * xw32;
-        if (c.best_remaining == 0)
-            pop->offer_solution(w, reinterpret_cast<const uint64_t*>(bestx.data() + off), c.best_value,
-                                c.best_loop);
-        else
-            pop->offer_advance(w, reinterpret_cast<const uint64_t*>(x0.data() + off), c.best_remaining,
-                               b->p.limit);
         if (status)
             status[l] = c.status;
         if (value)
@@ -679,6 +1182,16 @@ bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* 
             remaining[l] = c.best_remaining;
     }
     return BXG_OK;
+}
+
+int
+bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* status,
+                   double* value, int32_t* remaining)
+{
+    const int rc = bxg_optimize_reinit(b, pop, first_round, nullptr);
+    if (rc != BXG_OK)
+        return rc;
+    return bxg_optimize_run(b, pop, status, value, remaining);
 }
 
 uint64_t

@@ -256,6 +256,10 @@ void bxg_population_destroy(bxg_population* pop);
 int bxg_population_size(const bxg_population* pop);
 /* state of the master engine (after the constructor) */
 int bxg_population_master_state(bxg_population* pop, uint32_t* state);
+/* generate_seed (lib/src/itm-common.hpp:1457-1484) continuing the master engine,
+ * as optimize_problem does right after the constructor (:817): the seeds of
+ * `count` workers (bxg_population_worker_seed takes them as they are) */
+int bxg_population_generate_seeds(bxg_population* pop, int count, uint64_t* seeds);
 /* storage::get_best(i), :347-350: member at sorted position i */
 int bxg_population_member(bxg_population* pop, int i, uint64_t* x_words,
                           double* value, int* remaining, uint64_t* hash,
@@ -286,17 +290,38 @@ int bxg_population_try_advance(bxg_population* pop, int worker,
 int bxg_population_score(bxg_population* pop, const uint64_t* x_words, int count,
                          int32_t* remaining, double* value);
 /* One call of optimize_functor::operator()'s loop body (:658-750) for every
- * lane, the lanes being the workers: reinit (crossover / mutation of the
- * lane's x, kappa to start from) -> compute_order::init -> sweeps with the
- * kappa schedule -> push phase on the device -> try_update of the best
- * solution of the call or try_advance of the final x, in lane order.  The
- * Solver state (P, pi) persists between rounds; first_round = 1 starts from
- * x = 0, P = pi = 0.  Per call, a lane offers its best solution once (the
- * reference offers every solution it meets, each possibly drawing from the
- * worker's engine in the middle of the run).  Host outputs of n_lanes
- * entries, any may be NULL. */
+ * lane, the lanes being the workers, on the device:
+ *   reinit (:528-554)       the scalar draws (branch, parents, crossover masks,
+ *                           mutation rates: std::normal_distribution needs
+ *                           glibc's log) on the host from the engine state the
+ *                           lane ended its last call with; the crossover blocks
+ *                           and the per-variable mutation loop on the device
+ *                           (the Bernoulli stream consumed in parallel with the
+ *                           engine's jump-ahead), x never leaves the device;
+ *   compute_order::init, the sweeps with the kappa schedule, the push phase;
+ *   try_update (:571-584)   for EVERY solution met, where the reference offers
+ *                           it, inside the kernel: hash, can_be_inserted, the
+ *                           victim drawn from the lane's engine in the middle
+ *                           of the run, replace_result, sort -- the population
+ *                           lives in device memory, an insert holds its lock;
+ *   try_advance (:556-569)  with the run's last x when no solution was met.
+ * With one lane this is the reference's optimizer at thread = 1, restart by
+ * restart (tests/golden/optimizer_*.npz are traces of the compiled reference).
+ * With several lanes the inserts interleave in lock order, as the reference's
+ * threads do in mutex order.  The Solver state (P, pi) and x persist between
+ * calls; first_round = 1 starts from x = 0, P = pi = 0 and the workers' seeds.
+ * A finite time_limit of the batch's parameters stops the lanes at a sweep
+ * boundary (stop_task).  Host outputs of n_lanes entries, any may be NULL:
+ * status (0 a solution was met, 5 none, 3 stopped by the deadline), the value
+ * of the last solution, the smallest number of violated rows.
+ * bxg_optimize_round = bxg_optimize_reinit + bxg_optimize_run; the two halves
+ * are exposed as parity taps (state after reinit = state at the first sweep). */
 int bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round,
                        int32_t* status, double* value, int32_t* remaining);
+int bxg_optimize_reinit(bxg_batch* b, bxg_population* pop, int first_round,
+                        double* kappa);
+int bxg_optimize_run(bxg_batch* b, bxg_population* pop, int32_t* status,
+                     double* value, int32_t* remaining);
 /* bit_array_hash, bit-array.hpp:410-423 */
 uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
 
