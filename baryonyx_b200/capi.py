@@ -69,13 +69,15 @@ EXPORTS = [
     "bxg_batch_create", "bxg_batch_destroy", "bxg_batch_info", "bxg_batch_set_tail_value",
     "bxg_batch_begin", "bxg_batch_get_state", "bxg_batch_set_state", "bxg_batch_sweep",
     "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
-    "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_launches",
+    "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_device_ms", "bxg_batch_launches",
     "bxg_batch_words32", "bxg_batch_begin_device", "bxg_batch_set_lane_params",
     "bxg_population_create", "bxg_population_destroy", "bxg_population_size",
     "bxg_population_master_state", "bxg_population_generate_seeds", "bxg_population_member", "bxg_population_worker_seed",
     "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
     "bxg_population_mutation", "bxg_population_try_update", "bxg_population_try_advance",
     "bxg_population_score", "bxg_optimize_round", "bxg_optimize_reinit", "bxg_optimize_run",
+    "bxg_optimize", "bxg_population_stats", "bxg_comm_unique_id", "bxg_comm_init", "bxg_comm_destroy",
+    "bxg_comm_info", "bxg_exchange_best",
     "bxg_bit_array_hash",
     "bxg_lp_read", "bxg_lp_parse", "bxg_lp_destroy", "bxg_lp_info", "bxg_lp_rows", "bxg_lp_objective",
     "bxg_lp_variable", "bxg_lp_variables", "bxg_lp_names",
@@ -317,6 +319,13 @@ class Batch:
         check(lib().bxg_batch_last_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def device_ms(self) -> float:
+        """Device time of all timed launches since reset_counters (CUDA events)."""
+        ms = C.c_double()
+        lib().bxg_batch_device_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        check(lib().bxg_batch_device_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def launches(self) -> int:
         n = C.c_int64()
         check(lib().bxg_batch_launches(self.h, C.byref(n)))
@@ -352,11 +361,49 @@ def _bind_population(L):
     L.bxg_population_try_advance.argtypes = [C.c_void_p, C.c_int, _u64p, C.c_int, C.c_int64]
     L.bxg_population_score.argtypes = [C.c_void_p, _u64p, C.c_int, _i32p, _f64p]
     L.bxg_optimize_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bxg_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int, C.c_void_p,
+                               C.c_void_p, C.POINTER(C.c_int64)]
+    L.bxg_population_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.bxg_comm_unique_id.argtypes = [C.c_void_p]
+    L.bxg_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.bxg_comm_destroy.argtypes = [C.c_void_p]
+    L.bxg_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    L.bxg_exchange_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     L.bxg_optimize_reinit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.bxg_optimize_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bxg_bit_array_hash.argtypes = [C.c_int, _u64p]
     L.bxg_bit_array_hash.restype = C.c_uint64
     L._pop_bound = True
+
+
+UPDATE_FN = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_int64, C.c_double, C.c_int64, C.c_void_p)
+
+
+class Comm:
+    """bxg_comm: the NCCL communicator of the incumbent exchange (one per rank)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        _bind_population(lib())
+        buf = C.create_string_buffer(128)
+        check(lib().bxg_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, nranks: int, device: int):
+        _bind_population(lib())
+        self.h = C.c_void_p()
+        check(lib().bxg_comm_init(unique_id, rank, nranks, device, C.byref(self.h)))
+        self.rank, self.nranks = rank, nranks
+
+    def exchanges(self) -> int:
+        n = C.c_int64()
+        check(lib().bxg_comm_info(self.h, None, None, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().bxg_comm_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Population:
@@ -450,6 +497,29 @@ class Population:
         rem = np.zeros(batch.n_lanes, np.int32)
         check(lib().bxg_optimize_run(batch.h, self.h, _ptr(st), _ptr(val), _ptr(rem)))
         return {"status": st, "value": val, "remaining": rem}
+
+    def optimize(self, batch: "Batch", time_limit: float = 0.0, max_rounds: int = 0, comm: "Comm | None" = None,
+                 exchange_every: int = 0, update=None) -> int:
+        """bxg_optimize: rounds until the time limit or `max_rounds`; `update(remaining, value,
+        loop, duration, restarts)` about once a second.  Returns the rounds done."""
+        done = C.c_int64()
+        cb = None
+        if update is not None:
+            cb = UPDATE_FN(lambda rem, val, loop, dur, restarts, user: update(rem, val, loop, dur, restarts))
+        check(lib().bxg_optimize(batch.h, self.h, comm.h if comm else None, float(time_limit), int(max_rounds),
+                                 int(exchange_every), C.cast(cb, C.c_void_p) if cb else None, None,
+                                 C.byref(done)))
+        return done.value
+
+    def stats(self):
+        r, t = C.c_int64(), C.c_double()
+        check(lib().bxg_population_stats(self.h, C.byref(r), C.byref(t)))
+        return {"rounds": r.value, "first_solution_s": None if t.value < 0 else t.value}
+
+    def exchange(self, batch: "Batch", comm: "Comm", wait: bool = True):
+        w = C.c_int(-1)
+        check(lib().bxg_exchange_best(batch.h, self.h, comm.h, C.byref(w) if wait else None))
+        return w.value
 
     def hash(self, x: np.ndarray) -> int:
         return lib().bxg_bit_array_hash(self.n, x)

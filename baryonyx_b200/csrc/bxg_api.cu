@@ -9,6 +9,7 @@
 #include "bxg_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -176,6 +177,8 @@ struct bxg_batch
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0;
+    double total_ms = 0; // device time of all timed launches since the counters were reset
+    unsigned long long deadline_ns = 0; // stop_task for the kernels (bxg_optimize / time_limit)
     int64_t launches = 0;
     bool begun = false;
     std::vector<LaneCtl> h_ctl;
@@ -223,6 +226,7 @@ refresh_params(bxg_batch* b)
     q.pushing_iteration_limit = p.pushing_iteration_limit;
     q.order = p.order;
     q.tail_value = b->tail_value;
+    q.deadline_ns = b->deadline_ns;
     q.cost = b->d_norm_cost.p;
     q.powtab = b->d_powtab.p;
 }
@@ -899,6 +903,16 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(cudaMemset(b->d_bestx.p, 0, b->d_bestx.bytes()));
 
     b->cfg = plan_launch(pb->dev, pb->device, n_lanes);
+    {
+        // the row activities (4 m bytes) and the lane's control blocks always
+        // live in shared memory: refuse what cannot fit instead of failing at
+        // the first launch
+        int max_optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, pb->device));
+        if (b->cfg.smem > static_cast<size_t>(max_optin))
+            return fail(BXG_E_UNSUPPORTED,
+                        "problem too tall for one CTA's shared memory (row activities: 4 bytes per row)");
+    }
     if (!b->cfg.r_in_smem)
         CUDA_TRY(b->d_scratch.alloc(L * lane_scratch_bytes(pb->dev, b->cfg)));
     const size_t zbytes = z_scratch_bytes(pb->max_zrow);
@@ -1113,6 +1127,7 @@ run_begin(bxg_batch* b, const uint32_t* h_seeds, const uint32_t* d_x0, const uin
     b->launches += 1;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+    b->total_ms += b->last_ms;
     b->begun = true;
     return BXG_OK;
 }
@@ -1242,6 +1257,7 @@ bxg_batch_sweep(bxg_batch* b, int push, const double* kappa, double objective_am
     if (rc != BXG_OK)
         return rc;
     CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+    b->total_ms += b->last_ms;
     if (remaining)
         for (int l = 0; l != b->n_lanes; ++l)
             remaining[l] = b->h_ctl[l].remaining;
@@ -1286,6 +1302,7 @@ bxg_batch_solve(bxg_batch* b, int32_t* status, double* value, int32_t* remaining
     if (rc != BXG_OK)
         return rc;
     CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+    b->total_ms += b->last_ms;
     for (int l = 0; l != b->n_lanes; ++l) {
         const LaneCtl& c = b->h_ctl[l];
         if (status)
@@ -1387,6 +1404,8 @@ bxg_batch_reset_counters(bxg_batch* b)
     for (LaneCtl& c : b->h_ctl) {
         c.updates = 0;
         c.sweeps = 0;
+        c.offers = 0;
+        c.inserts = 0;
         c.alg_bytes = 0;
         for (int i = 0; i < 4; ++i) {
             c.n_path[i] = 0;
@@ -1396,6 +1415,7 @@ bxg_batch_reset_counters(bxg_batch* b)
     }
     CUDA_TRY(cudaMemcpy(b->d_ctl.p, b->h_ctl.data(), sizeof(LaneCtl) * b->n_lanes,
                         cudaMemcpyHostToDevice));
+    b->total_ms = 0;
     return BXG_OK;
 }
 
@@ -1486,6 +1506,15 @@ bxg_batch_last_ms(bxg_batch* b, float* ms)
     if (!b || !ms)
         return fail(BXG_E_INVALID, "bxg_batch_last_ms: bad argument");
     *ms = b->last_ms;
+    return BXG_OK;
+}
+
+int
+bxg_batch_device_ms(bxg_batch* b, double* total_ms)
+{
+    if (!b || !total_ms)
+        return fail(BXG_E_INVALID, "bxg_batch_device_ms: bad argument");
+    *total_ms = b->total_ms;
     return BXG_OK;
 }
 

@@ -1354,16 +1354,46 @@ violated_scan(Lane& L, int mode)
 {
     const DevProblem& pb = *L.pb;
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int m = pb.m;
 
-    // ordered compaction by warp 0
-    if (warp == 0) {
-        int count = 0;
-        for (int base = 0; base < pb.m; base += 32) {
-            const int k = base + lane;
+    // ordered compaction: every warp takes a contiguous share of the rows
+    // (whole groups of 32), counts its violated rows, and after the prefix over
+    // the warps writes them in place
+    const int groups = (m + 31) >> 5;
+    const int per_warp = (groups + nw - 1) / nw;
+    const int g0 = warp * per_warp;
+    const int g1 = min(groups, g0 + per_warp);
+    const int* __restrict__ bmin = pb.bmin;
+    const int* __restrict__ bmax = pb.bmax;
+
+    int mine = 0;
+    for (int g = g0; g < g1; ++g) {
+        const int k = (g << 5) + lane;
+        int amount = 0;
+        if (k < m) {
+            const int v = L.act[k], lo = bmin[k], hi = bmax[k];
+            amount = lo > v ? lo - v : (hi < v ? v - hi : 0);
+        }
+        mine += __popc(__ballot_sync(0xffffffffu, amount != 0));
+    }
+    if (lane == 0)
+        L.sh->redi[warp] = mine;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nw; ++w) {
+        const int v = L.sh->redi[w];
+        if (w < warp)
+            before += v;
+        total += v;
+    }
+    if (mode != 2 && mine) {
+        int count = before;
+        for (int g = g0; g < g1; ++g) {
+            const int k = (g << 5) + lane;
             int amount = 0;
-            if (k < pb.m) {
-                const int v = L.act[k], lo = pb.bmin[k], hi = pb.bmax[k];
+            if (k < m) {
+                const int v = L.act[k], lo = bmin[k], hi = bmax[k];
                 amount = lo > v ? lo - v : (hi < v ? v - hi : 0);
             }
             const unsigned mask = __ballot_sync(0xffffffffu, amount != 0);
@@ -1371,22 +1401,22 @@ violated_scan(Lane& L, int mode)
                 const int pos = count + __popc(mask & ((1u << lane) - 1u));
                 if (mode == 0)
                     L.oR[pos] = k;
-                else if (mode == 1)
+                else
                     L.mo[pos] = make_int2(k, amount);
             }
             count += __popc(mask);
         }
-        if (lane == 0) {
-            L.sh->remaining = count;
-            if (mode == 0)
-                L.sh->list_len = count;
-            else if (mode == 1)
-                L.sh->tmp_i = count;
-            L.alg_bytes += 12.0 * pb.m;
-        }
+    }
+    if (tid == 0) {
+        L.sh->remaining = total;
+        if (mode == 0)
+            L.sh->list_len = total;
+        else if (mode == 1)
+            L.sh->tmp_i = total;
+        L.alg_bytes += 12.0 * m;
     }
     __syncthreads();
-    return L.sh->remaining;
+    return total;
 }
 
 // Lane-local list lengths live in registers of every thread (uniform).
@@ -1485,6 +1515,11 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     const int len = pairs ? ls.mo_len : ls.oR_len;
     if (tid == 0)
         L.updates += len;
+    // An empty list is the list of violated rows of an x that has none: the
+    // sweep changes nothing and the scan would find what the last one found
+    // (the skipped scan is not counted as algorithmic bytes).
+    if (len == 0 && order != ORDER_PI_SIGN_CHANGE)
+        return 0;
     for (int i = 0; i < len; ++i) {
         int k;
         if (pairs)
@@ -2021,14 +2056,9 @@ pop_offer(Lane& L, const DevBatch& b, bool solution, int remaining, long long lo
     const double value = sh->x_value;
     const unsigned long long hash = sh->x_hash;
 
-    if (tid == 0) {
-        L.offers += 1;
-        while (atomicCAS(pop.lock, 0, 1) != 0)
-            __nanosleep(64);
-        __threadfence();
-    }
-    __syncthreads();
-
+    // can_be_inserted (:302-326) reads the scores without the writers' lock,
+    // like the reference (a shared lock there): a lane in the feasible regime
+    // offers the same x sweep after sweep and must not queue for that
     int found = 0;
     for (int i = tid; i < pop.size; i += T) {
         const int r = ld_vol(pop.remaining + i);
@@ -2039,8 +2069,19 @@ pop_offer(Lane& L, const DevBatch& b, bool solution, int remaining, long long lo
             found |= (r == remaining && h == hash);
     }
     found = __syncthreads_or(found);
+    if (tid == 0)
+        L.offers += 1;
+    if (found)
+        return;
 
-    if (!found) {
+    if (tid == 0) {
+        while (atomicCAS(pop.lock, 0, 1) != 0)
+            __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+
+    {
         if (tid == 0) {
             // choose_a_bad_solution: uniform_int_distribution<int>(size / 5, size - 1)
             uint32_t rng = sh->rng;
@@ -2057,6 +2098,8 @@ pop_offer(Lane& L, const DevBatch& b, bool solution, int remaining, long long lo
             pop.hash[id] = hash;
             pop.loop[id] = loop;
             pop.duration[id] = (double)(now - pop.t0_ns) * 1e-9;
+            if (solution)
+                atomicMin(pop.first_ns, now - pop.t0_ns);
             L.inserts += 1;
         }
         __syncthreads();

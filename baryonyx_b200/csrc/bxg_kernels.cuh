@@ -157,6 +157,7 @@ struct DevPop
     int* order;               // [size] m_indices
     int* lock;
     const uint32_t* bastert;  // [xw32] m_bastert
+    unsigned long long* first_ns; // device-clock time of the first solution a lane offered
     unsigned long long t0_ns;
 };
 

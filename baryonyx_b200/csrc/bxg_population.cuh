@@ -344,6 +344,7 @@ struct bxg_population
     DevBuf<int> d_premaining, d_porder, d_plock;
     DevBuf<unsigned long long> d_phash;
     DevBuf<long long> d_ploop;
+    DevBuf<unsigned long long> d_pfirst;
     DevBuf<ReinitPlan> d_plan;
     DevBuf<unsigned long long> d_masks, d_aux;
     std::vector<ReinitPlan> plans;
@@ -366,6 +367,7 @@ struct bxg_population
         v.order = d_porder.p;
         v.lock = d_plock.p;
         v.bastert = d_bastert.p;
+        v.first_ns = d_pfirst.p;
         v.t0_ns = t0_ns;
         return v;
     }
@@ -383,6 +385,8 @@ struct bxg_population
             CUDA_TRY(d_plock.alloc(1));
             CUDA_TRY(d_phash.alloc(size));
             CUDA_TRY(d_ploop.alloc(size));
+            CUDA_TRY(d_pfirst.alloc(1));
+            CUDA_TRY(cudaMemset(d_pfirst.p, 0xff, sizeof(unsigned long long)));
             CUDA_TRY(cudaMemset(d_plock.p, 0, sizeof(int)));
             CUDA_TRY(cudaMemset(d_pduration.p, 0, sizeof(double) * size));
             CUDA_TRY(cudaMemcpy(d_bastert.p, bastert.data(), sizeof(uint64_t) * words,
@@ -1161,6 +1165,7 @@ bxg_optimize_run(bxg_batch* b, bxg_population* pop, int32_t* status, double* val
     CUDA_TRY(cudaSetDevice(pb->device));
     const int L = b->n_lanes;
     pop->reinit_done = false;
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream)); // the dominant kernel alone (roofline)
     launch_optimize(pb->dev, b->prm, b->dev, b->cfg, b->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
@@ -1171,6 +1176,7 @@ bxg_optimize_run(bxg_batch* b, bxg_population* pop, int32_t* status, double* val
     if (rc != BXG_OK)
         return rc;
     CUDA_TRY(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+    b->total_ms += b->last_ms;
 
     for (int l = 0; l != L; ++l) {
         const LaneCtl& c = b->h_ctl[l];
@@ -1194,10 +1200,389 @@ bxg_optimize_round(bxg_batch* b, bxg_population* pop, int first_round, int32_t* 
     return bxg_optimize_run(b, pop, status, value, remaining);
 }
 
+int
+bxg_optimize(bxg_batch* b, bxg_population* pop, bxg_comm* comm, double time_limit,
+             int64_t max_rounds, int exchange_every, bxg_update_fn update, void* user,
+             int64_t* rounds_done)
+{
+    if (!b || !pop || pop->pb != b->pb)
+        return fail(BXG_E_INVALID, "bxg_optimize: batch and population of different problems");
+    if (!(time_limit > 0) && max_rounds <= 0)
+        return fail(BXG_E_INVALID, "bxg_optimize: neither a time limit nor a number of rounds");
+    CUDA_TRY(cudaSetDevice(b->pb->device));
+    const auto start = std::chrono::steady_clock::now();
+    auto last_report = start;
+    auto elapsed = [&] {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    };
+
+    b->deadline_ns = 0;
+    if (time_limit > 0) {
+        // stop_task for the kernels: the lanes leave their loops at the first
+        // sweep boundary past the deadline (device clock)
+        unsigned long long now = 0;
+        unsigned long long* d_now = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_now), sizeof(unsigned long long), b->stream));
+        k_globaltimer<<<1, 1, 0, b->stream>>>(d_now);
+        CUDA_TRY(cudaMemcpyAsync(&now, d_now, sizeof(now), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        CUDA_TRY(cudaFreeAsync(d_now, b->stream));
+        b->deadline_ns = now + static_cast<unsigned long long>(time_limit * 1e9);
+    }
+
+    int64_t rounds = 0;
+    int rc = BXG_OK;
+    for (;;) {
+        rc = bxg_optimize_round(b, pop, pop->rounds == 0 ? 1 : 0, nullptr, nullptr, nullptr);
+        if (rc != BXG_OK)
+            break;
+        ++rounds;
+        if (comm && exchange_every > 0 && rounds % exchange_every == 0) {
+            rc = bxg_exchange_best(b, pop, comm, nullptr);
+            if (rc != BXG_OK)
+                break;
+        }
+        const auto now = std::chrono::steady_clock::now();
+        if (update && std::chrono::duration<double>(now - last_report).count() >= 1.0) {
+            // optimize_problem's once-a-second report, itm-optimizer-common.hpp:835-853
+            last_report = now;
+            rc = pop->fetch_scores(b->stream);
+            if (rc != BXG_OK)
+                break;
+            const bxg_population::member& best = pop->data[pop->order[0]];
+            update(best.remaining, best.value, best.loop, elapsed(), pop->rounds * b->n_lanes, user);
+        }
+        if (max_rounds > 0 && rounds >= max_rounds)
+            break;
+        if (time_limit > 0 && elapsed() >= time_limit)
+            break;
+    }
+    b->deadline_ns = 0;
+    if (rounds_done)
+        *rounds_done = rounds;
+    return rc;
+}
+
+int
+bxg_population_stats(bxg_population* pop, int64_t* rounds, double* first_solution_seconds)
+{
+    if (!pop)
+        return fail(BXG_E_INVALID, "null population");
+    if (rounds)
+        *rounds = pop->rounds;
+    if (first_solution_seconds) {
+        *first_solution_seconds = -1.0;
+        if (pop->d_pfirst.p) {
+            CUDA_TRY(cudaSetDevice(pop->pb->device));
+            CUDA_TRY(cudaDeviceSynchronize());
+            unsigned long long ns = 0;
+            CUDA_TRY(cudaMemcpy(&ns, pop->d_pfirst.p, sizeof(ns), cudaMemcpyDeviceToHost));
+            if (ns != ~0ull)
+                *first_solution_seconds = static_cast<double>(ns) * 1e-9;
+        }
+    }
+    return BXG_OK;
+}
+
 uint64_t
 bxg_bit_array_hash(int n, const uint64_t* x_words)
 {
     return bxg_population::hash_of(x_words, n / 64 + 1);
+}
+
+
+// ---------------------------------------------------------------------------
+// multi-GPU: the incumbent exchange
+// ---------------------------------------------------------------------------
+} // extern "C"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+// NCCL is bound at run time: a process that never calls bxg_comm_* does not
+// need the library, and inside a torch process the already loaded
+// libnccl.so.2 is the one that answers.
+struct nccl_api
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+
+    bool load()
+    {
+        if (handle)
+            return true;
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle)
+                break;
+        }
+        if (!handle) {
+            error = std::string("libnccl.so.2 not found: ") + dlerror();
+            return false;
+        }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(handle, "ncclAllGather"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) {
+            error = "libnccl.so.2 lacks an entry point";
+            handle = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+
+nccl_api g_nccl;
+
+#define NCCL_TRY(expr)                                                                           \
+    do {                                                                                         \
+        ncclResult_t r_ = (expr);                                                                \
+        if (r_ != ncclSuccess)                                                                   \
+            return fail(BXG_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r_));      \
+    } while (0)
+
+// What a rank sends: its best member.
+struct IncumbentHdr
+{
+    int remaining;
+    int rank;
+    double value;
+    unsigned long long hash;
+    long long loop;
+};
+
+// storage::sort's comparator, itm-optimizer-common.hpp:427-441
+struct MemberLess
+{
+    const int* rem;
+    const double* val;
+    bool maximize;
+    __device__ bool operator()(const int& a, const int& b) const
+    {
+        if (rem[a] < rem[b])
+            return true;
+        if (rem[a] == rem[b])
+            return maximize ? val[a] > val[b] : val[a] < val[b];
+        return false;
+    }
+};
+
+// best member of the local population -> send buffer
+__global__ void __launch_bounds__(256)
+k_pack_incumbent(const __grid_constant__ DevPop pop, int xw32, int rank, unsigned char* out)
+{
+    const int id = pop.order[0];
+    if (threadIdx.x == 0) {
+        IncumbentHdr h;
+        h.remaining = pop.remaining[id];
+        h.rank = rank;
+        h.value = pop.value[id];
+        h.hash = pop.hash[id];
+        h.loop = pop.loop[id];
+        *reinterpret_cast<IncumbentHdr*>(out) = h;
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + sizeof(IncumbentHdr));
+    const uint32_t* src = pop.x + (size_t)id * xw32;
+    for (int w = threadIdx.x; w < xw32; w += blockDim.x)
+        dst[w] = src[w];
+}
+
+// The box-wide incumbent (fewest remaining constraints, then the better
+// objective, then the lowest rank: raw_result's order,
+// itm-optimizer-common.hpp:427-441) replaces the worst member of the local
+// population unless the population already holds it; the order is rebuilt with
+// storage::sort.  One CTA.
+__global__ void __launch_bounds__(256)
+k_adopt_incumbent(const __grid_constant__ DevPop pop, int xw32, int rank, int nranks, int maximize,
+                  const unsigned char* gathered, size_t stride, int* winner_out)
+{
+    __shared__ int s_win, s_take, s_slot;
+    __shared__ double s_val[256];
+    __shared__ int s_rem[256];
+    __shared__ int s_ord[256];
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) {
+        int win = 0;
+        IncumbentHdr best = *reinterpret_cast<const IncumbentHdr*>(gathered);
+        for (int r = 1; r < nranks; ++r) {
+            const IncumbentHdr h = *reinterpret_cast<const IncumbentHdr*>(gathered + stride * r);
+            bool better = false;
+            if (h.remaining != best.remaining)
+                better = h.remaining < best.remaining;
+            else if (h.value != best.value)
+                better = maximize ? h.value > best.value : h.value < best.value;
+            if (better) {
+                best = h;
+                win = r;
+            }
+        }
+        s_win = win;
+        int take = win != rank;
+        for (int i = 0; take && i < pop.size; ++i)
+            if (pop.remaining[i] == best.remaining && pop.hash[i] == best.hash &&
+                (best.remaining != 0 || pop.value[i] == best.value))
+                take = 0;
+        s_take = take;
+        const int slot = pop.order[pop.size - 1];
+        s_slot = slot;
+        if (take) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            pop.remaining[slot] = best.remaining;
+            pop.value[slot] = best.value;
+            pop.hash[slot] = best.hash;
+            pop.loop[slot] = best.loop;
+            pop.duration[slot] = (double)(now - pop.t0_ns) * 1e-9;
+        }
+        if (winner_out)
+            *winner_out = win;
+    }
+    __syncthreads();
+    if (!s_take)
+        return;
+    const uint32_t* src =
+      reinterpret_cast<const uint32_t*>(gathered + stride * s_win + sizeof(IncumbentHdr));
+    uint32_t* dst = pop.x + (size_t)s_slot * xw32;
+    for (int w = tid; w < xw32; w += T)
+        dst[w] = src[w];
+    for (int i = tid; i < pop.size; i += T) {
+        s_val[i] = pop.value[i];
+        s_rem[i] = pop.remaining[i];
+        s_ord[i] = pop.order[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        seq_std_sort(Plain<int>{ s_ord }, pop.size, MemberLess{ s_rem, s_val, maximize != 0 });
+    }
+    __syncthreads();
+    for (int i = tid; i < pop.size; i += T)
+        pop.order[i] = s_ord[i];
+}
+
+} // namespace
+
+struct bxg_comm
+{
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1, device = 0;
+    DevBuf<unsigned char> d_send, d_recv;
+    DevBuf<int> d_winner;
+    size_t stride = 0;
+    int64_t exchanges = 0;
+};
+
+extern "C" {
+
+int
+bxg_comm_unique_id(void* id128)
+{
+    if (!id128)
+        return fail(BXG_E_INVALID, "bxg_comm_unique_id: null buffer");
+    if (!g_nccl.load())
+        return fail(BXG_E_UNSUPPORTED, g_nccl.error);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    return BXG_OK;
+}
+
+int
+bxg_comm_init(const void* id128, int rank, int nranks, int device, bxg_comm** out)
+{
+    if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(BXG_E_INVALID, "bxg_comm_init: bad argument");
+    if (!g_nccl.load())
+        return fail(BXG_E_UNSUPPORTED, g_nccl.error);
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<bxg_comm> c(new (std::nothrow) bxg_comm);
+    if (!c)
+        return fail(BXG_E_MEMORY, "out of host memory");
+    c->rank = rank;
+    c->nranks = nranks;
+    c->device = device;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    CUDA_TRY(c->d_winner.alloc(1));
+    *out = c.release();
+    return BXG_OK;
+}
+
+void
+bxg_comm_destroy(bxg_comm* c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.handle)
+        g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+int
+bxg_comm_info(const bxg_comm* c, int* rank, int* nranks, int64_t* exchanges)
+{
+    if (!c)
+        return fail(BXG_E_INVALID, "null communicator");
+    if (rank)
+        *rank = c->rank;
+    if (nranks)
+        *nranks = c->nranks;
+    if (exchanges)
+        *exchanges = c->exchanges;
+    return BXG_OK;
+}
+
+int
+bxg_exchange_best(bxg_batch* b, bxg_population* pop, bxg_comm* c, int* winner_rank)
+{
+    if (!b || !pop || !c || pop->pb != b->pb)
+        return fail(BXG_E_INVALID, "bxg_exchange_best: bad argument");
+    if (pop->size > 256)
+        return fail(BXG_E_UNSUPPORTED, "bxg_exchange_best: population larger than 256");
+    bxg_problem* pb = b->pb;
+    CUDA_TRY(cudaSetDevice(pb->device));
+    if (pop->host_newer) {
+        int rc = pop->to_device(b->stream);
+        if (rc != BXG_OK)
+            return rc;
+    }
+    const int xw32 = pb->dev.xw32;
+    const size_t stride = (sizeof(IncumbentHdr) + sizeof(uint32_t) * xw32 + 15) & ~size_t(15);
+    if (c->stride != stride) {
+        CUDA_TRY(c->d_send.alloc(stride));
+        CUDA_TRY(c->d_recv.alloc(stride * c->nranks));
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        c->stride = stride;
+    }
+    // everything on the batch's stream, no host synchronisation: the next
+    // round's kernels queue behind the adoption
+    const DevPop view = pop->dev_view();
+    k_pack_incumbent<<<1, 256, 0, b->stream>>>(view, xw32, c->rank, c->d_send.p);
+    NCCL_TRY(g_nccl.AllGather(c->d_send.p, c->d_recv.p, stride, ncclChar, c->comm, b->stream));
+    k_adopt_incumbent<<<1, 256, 0, b->stream>>>(view, xw32, c->rank, c->nranks, pb->maximize,
+                                                c->d_recv.p, stride, c->d_winner.p);
+    CUDA_TRY(cudaGetLastError());
+    b->launches += 2;
+    c->exchanges += 1;
+    pop->device_newer = true;
+    if (winner_rank) {
+        CUDA_TRY(cudaMemcpyAsync(winner_rank, c->d_winner.p, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return BXG_OK;
 }
 
 } // extern "C"

@@ -4,15 +4,23 @@
     python bench.py --gpus N --steps K --warmup W            # this engine
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
 
-A *step* is one pass of the hot path over one batch: `lanes` independent
-restarts (one Solver instance each: P, pi, x, random engine) of the workload,
-each running the reference's solver_functor loop (lib/src/itm-solver-common.hpp
-:135-225) for `limit` sweeps -- bxg_batch_begin + bxg_batch_solve through the
-C ABI (include/bxg.h).  Workload at N=1 = BASELINE.json configs[1]: the
-SPP-shaped 500 x 10 000 set-partitioning instance, 1024 batched restarts.
-For N>1 every rank runs its own `lanes` restarts (weak scaling, no data-path
-collective: restarts are independent; only the final best-objective reduce
-goes over NCCL).
+Default (--mode optimize): the reference's OPTIMIZER on the workload, its
+workers batched as lanes.  A *step* is `--rounds` calls of every worker's loop
+body (optimize_functor::operator(), lib/src/itm-optimizer-common.hpp:658-750:
+reinit by crossover / mutation from the shared population, the sweeps with the
+kappa schedule, the push phase, every solution offered to the population) --
+bxg_optimize through the C ABI (include/bxg.h), population and lanes resident
+in HBM.  Workload at N=1 = BASELINE.json configs[1]: the SPP-shaped
+500 x 10 000 set-partitioning instance, 1024 workers.  For N>1 every rank runs
+its own `lanes` workers on its own copy of the population (weak scaling) and
+the incumbent exchange -- one ncclAllGather of the ranks' best members on the
+batch's stream, bxg_exchange_best -- runs INSIDE the timed region every
+`--exchange-every` rounds.  The reference arm runs the reference's own
+optimize_problem on all host threads.
+
+--mode solve is round 1's workload: `lanes` independent restarts of
+solver_functor (lib/src/itm-solver-common.hpp:135-225) for `limit` sweeps,
+bxg_batch_begin + bxg_batch_solve.
 
 The JSON line carries the device-resident number (`value`), the end-to-end
 number through the C ABI with host buffers (`e2e`), the roofline of the
@@ -51,11 +59,21 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="spp", choices=["spp", "scp", "csplib022", "telebus", "rail-small", "rail"])
     ap.add_argument("--lanes", type=int, default=1024, help="restarts per GPU per step")
-    ap.add_argument("--limit", type=int, default=100, help="sweeps per restart (solver_parameters.limit)")
+    ap.add_argument("--mode", default="optimize", choices=["optimize", "solve"])
+    ap.add_argument("--limit", type=int, default=0,
+                    help="sweeps per restart (solver_parameters.limit); 0 = the reference's default 1000 in "
+                         "optimize mode, 100 in solve mode")
+    ap.add_argument("--rounds", type=int, default=1, help="optimizer rounds per step (optimize mode)")
+    ap.add_argument("--exchange-every", type=int, default=1, help="incumbent exchange every this many rounds (N>1)")
+    ap.add_argument("--seed", type=int, default=42, help="solver_parameters.seed of the optimizer")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="time_limit of one reference optimizer run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-lanes", type=int, default=0, help="restarts in the CPU sample (0 = 2 x cores)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.limit <= 0:
+        args.limit = 1000 if args.mode == "optimize" else 100
+    return args
 
 
 def make_instance(name):
@@ -83,7 +101,7 @@ def bench_params(args, mod):
     return mod.clamp_params(p)
 
 
-def measured_traffic(workload, lanes, limit):
+def measured_traffic(workload, lanes, limit, mode="solve"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_solve launch from
     the committed `ncu --set full` capture of this same workload
     (profiles/traffic.json, written from the .ncu-rep by profiles/ncu_summary.sh);
@@ -91,7 +109,7 @@ def measured_traffic(workload, lanes, limit):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             d = json.load(f)
-        if (d.get("workload"), d.get("lanes"), d.get("limit")) == (workload, lanes, limit):
+        if (d.get("workload"), d.get("lanes"), d.get("limit"), d.get("mode", "solve")) == (workload, lanes, limit, mode):
             return float(d["dram_bytes_per_launch"])
     except Exception:
         pass
@@ -255,8 +273,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wname, "lanes_per_gpu": args.lanes, "limit": args.limit,
-                   "mode": "solve (solver_functor per restart)"},
+        "config": config_of(args, wname, inst),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -439,10 +456,7 @@ def run_engine(args):
             "device_ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": wname, "lanes_per_gpu": L, "limit": args.limit,
-                       "mode": "solve (solver_functor per restart)", "m": inst["m"], "n": inst["n"],
-                       "nnz": nnz, "l2": "inputs larger than L2 (P is %.0f MB per GPU)" % (L * nnz * 8 / 1e6),
-                       "device_bytes": info["device_bytes"]},
+            "config": config_of(args, wname, inst), "device_bytes": info["device_bytes"],
             "sweeps_per_s": sweeps / wall_max,
             "best": {"remaining": inc_rem, "value": inc_value if inc_rem == 0 else None, "rank": winner,
                      "ones": int(np.unpackbits(inc_x.view(np.uint8)).sum())},
@@ -472,11 +486,290 @@ def run_engine(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------
+# optimizer mode
+# ---------------------------------------------------------------------------
+def config_of(args, wname, inst):
+    """The `config` object: the same keys and values in both arms."""
+    nnz = int(inst["row_ptr"][-1])
+    if args.mode == "optimize":
+        return {"workload": wname, "mode": "optimize (optimize_functor per worker, shared population)",
+                "workers_per_gpu": args.lanes, "limit": args.limit, "rounds_per_step": args.rounds,
+                "exchange_every": args.exchange_every, "seed": args.seed, "m": inst["m"], "n": inst["n"],
+                "nnz": nnz, "l2": "inputs larger than L2 (P is %.0f MB per GPU)" % (args.lanes * nnz * 8 / 1e6)}
+    return {"workload": wname, "mode": "solve (solver_functor per restart)", "lanes_per_gpu": args.lanes,
+            "limit": args.limit, "m": inst["m"], "n": inst["n"], "nnz": nnz,
+            "l2": "inputs larger than L2 (P is %.0f MB per GPU)" % (args.lanes * nnz * 8 / 1e6)}
+
+
+def cpu_optimize_sample(inst, args, seconds, seed):
+    """The reference's own optimize_problem<> (all host threads, counting Solver
+    subclass) on the workload for `seconds`: the faster of its two builds
+    (-O2 parity flags without contract checks, and the
+    reference's release flags -O3 + FMA).  Returns a dict."""
+    from baryonyx_b200 import synth
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    p = po.default_params()
+    p.limit = args.limit
+    flavours = [f for f in (True, "o3") if po.ref_available(f)]
+    if not flavours:
+        raise SystemExit("bench.py: oracle/_ref is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    runs = []
+    for fl in flavours:
+        pb = po.RefProblem(None, p, fast=fl, inst=inst)
+        r = pb.optimize(seed, cores, seconds)
+        pb.close()
+        r["flavour"] = "-O3 -march=x86-64-v3, FMA, no contract checks" if fl == "o3" else \
+            "-O2 -ffp-contract=off, no contract checks"
+        r["rate"] = r["updates"] / r["seconds"]
+        r["threads"] = cores
+        del r["x"]
+        runs.append(r)
+    runs.sort(key=lambda r: -r["rate"])
+    out = runs[0]
+    out["other"] = runs[1] if len(runs) > 1 else None
+    return out
+
+
+def run_reference_optimize(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    inst, wname = make_instance(args.workload)
+    seconds = args.cpu_seconds or 8.0
+    for w in range(min(args.warmup, 1)):
+        cpu_optimize_sample(inst, args, 2.0, args.seed)
+    upd = swp = 0
+    sec = 0.0
+    best = None
+    r = None
+    for s in range(args.steps):
+        r = cpu_optimize_sample(inst, args, seconds, args.seed + s)
+        upd += r["updates"]
+        swp += r["sweeps"]
+        sec += r["seconds"]
+        best = r
+    value = upd / sec
+    sample = (f"optimize_problem, {r['threads']} host threads, time_limit {seconds:.0f} s per step, "
+              f"{r['flavour']} (the faster build)")
+    if r.get("other"):
+        sample += f"; the other build: {r['other']['rate']:.3g} updates/s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(args, wname, inst),
+        "sweeps_per_s": swp / sec,
+        "best": {"remaining": best["remaining"], "value": best["value"] if best["remaining"] == 0 else None},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_engine_optimize(args):
+    import torch
+    import torch.distributed as dist
+
+    from baryonyx_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the engine's own communicator (bxg_comm_init): rank 0 creates the NCCL id,
+        # torch.distributed only carries its 128 bytes to the other ranks
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident = torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(ident, 0)
+        comm = capi.Comm(bytes(ident.cpu().numpy().tobytes()), rank, world, local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    inst, wname = make_instance(args.workload)
+    cp = bench_params(args, capi)
+    cp.seed = args.seed
+    L = args.lanes
+
+    def make_optimizer(instance):
+        """Problem, batch, population and worker seeds as optimize_problem sets them
+        up (itm-optimizer-common.hpp:793-826): every rank builds the same population
+        from the master seed and keeps its own slice of the workers' seeds."""
+        pb = capi.Problem(instance, device=local)
+        bt = pb.batch(L, cp)
+        pop = capi.Population(pb, cp, args.seed, workers=L)
+        seeds = pop.generate_seeds(world * L)
+        for l in range(L):
+            pop.ctx(l, int(seeds[rank * L + l]))
+        return pb, bt, pop
+
+    pb, bt, pop = make_optimizer(inst)
+    info = bt.info()
+
+    def one_step():
+        pop.optimize(bt, max_rounds=args.rounds, comm=comm, exchange_every=args.exchange_every)
+
+    for s in range(args.warmup):
+        one_step()
+
+    bt.reset_counters()
+    launches0 = bt.launches()
+    exchanges0 = comm.exchanges() if comm else 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        one_step()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = bt.counters()
+    dev_ms = bt.device_ms()
+    launches = bt.launches() - launches0
+    exchanges = (comm.exchanges() - exchanges0) if comm else 0
+    stats = pop.stats()
+    best = pop.member(0)
+
+    t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(cnt["updates"]), float(cnt["sweeps"]), cnt["algorithmic_bytes"], float(launches)],
+                     dtype=torch.float64, device="cuda")
+    fs = stats["first_solution_s"]
+    f = torch.tensor([fs if fs is not None else float("inf")], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    wall_max, dev_ms_max = t.tolist()
+    updates, sweeps, alg_bytes, launches_all = w.tolist()
+    first_solution = f.item()
+
+    # ---- end to end through the C ABI with host buffers ---------------------
+    e2e = None
+    if not args.no_e2e:
+        keys = ("row_ptr", "col", "factor", "cmin", "cmax", "obj_var", "obj_factor")
+        hinst = dict(inst)
+        for k in keys:
+            hinst[k] = pinned_like(inst[k])
+        h2d = sum(hinst[k].nbytes for k in keys)
+        split = [0.0] * 4
+
+        def e2e_step():
+            """What a caller of the C ABI does: merged constraints from host memory to
+            a new problem, batch and population (built on the host from the master
+            seed, scored and kept on the device), the rounds, the best member and the
+            population's scores back to the host."""
+            t0 = time.perf_counter()
+            pb2, bt2, pop2 = make_optimizer(hinst)
+            t1 = time.perf_counter()
+            pop2.optimize(bt2, max_rounds=args.rounds, comm=comm, exchange_every=args.exchange_every)
+            t2 = time.perf_counter()
+            top = pop2.member(0)
+            upd = bt2.counters()["updates"]
+            nbytes = top["x"].nbytes + 40 * pop2.size()
+            t3 = time.perf_counter()
+            pop2.close()
+            bt2.close()
+            pb2.close()
+            t4 = time.perf_counter()
+            for i, (a, b) in enumerate(zip((t0, t1, t2, t3), (t1, t2, t3, t4))):
+                split[i] += 1e3 * (b - a)
+            return upd, nbytes
+
+        e2e_step()  # untimed warm-up (allocator, first-use costs)
+        split = [0.0] * 4
+        e2e_updates = 0
+        d2h = 0
+        barrier()
+        te = time.perf_counter()
+        for s in range(args.steps):
+            upd, d2h = e2e_step()
+            e2e_updates += upd
+        barrier()
+        e2e_wall = time.perf_counter() - te
+        te_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+        eu_t = torch.tensor([float(e2e_updates)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(eu_t, op=dist.ReduceOp.SUM)
+        e2e = {"value": eu_t.item() / te_t.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * te_t.item() / args.steps,
+               "note": "every step starts a new optimizer from x = 0 (first restarts: all rows violated)",
+               "split_ms_per_step": dict(zip(("create", "rounds", "results", "destroy"),
+                                             [round(v / args.steps, 2) for v in split]))}
+
+    pop.close()
+    bt.close()
+    pb.close()
+    if comm:
+        comm.close()
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        n_launch = args.steps * args.rounds
+        per_launch_bytes = cnt["algorithmic_bytes"] / n_launch
+        per_launch_s = dev_ms / n_launch / 1e3
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        restarts = world * L * args.steps * args.rounds
+        line = {
+            "metric": METRIC, "value": updates / wall_max, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps,
+            "device_ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_of(args, wname, inst),
+            "device_bytes": info["device_bytes"],
+            "sweeps_per_s": sweeps / wall_max, "restarts_per_s": restarts / wall_max,
+            "algorithmic_bytes_per_s": alg_bytes / wall_max,
+            "time_to_feasible_s": None if first_solution == float("inf") else first_solution,
+            "exchanges_in_timed_region": int(exchanges),
+            "best": {"remaining": best["remaining"], "value": best["value"] if best["remaining"] == 0 else None},
+            "roofline": {"bound": "hbm", "kernel": "k_optimize", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                         "traffic": measured_traffic(args.workload, L, args.limit, "optimize"),
+                         "bytes_per_launch": per_launch_bytes, "ms_per_launch": 1e3 * per_launch_s},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            secs = args.cpu_seconds or 12.0
+            r = cpu_optimize_sample(inst, args, secs, args.seed)
+            line["cpu_baseline"] = {
+                "value": r["rate"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                "sample": f"optimize_problem for {r['seconds']:.1f} s on {r['threads']} host threads, {r['flavour']}"
+                          + (f"; the other build: {r['other']['rate']:.3g} updates/s" if r.get("other") else ""),
+            }
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
-        return run_reference(args)
-    return run_engine(args)
+        return run_reference_optimize(args) if args.mode == "optimize" else run_reference(args)
+    return run_engine_optimize(args) if args.mode == "optimize" else run_engine(args)
 
 
 if __name__ == "__main__":

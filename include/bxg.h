@@ -227,6 +227,9 @@ int bxg_batch_set_lane_params(bxg_batch* b, const double* theta,
 /* Device time of the last bxg_batch_sweep / bxg_batch_solve, CUDA events on
  * the batch's stream, milliseconds. */
 int bxg_batch_last_ms(bxg_batch* b, float* ms);
+/* The same summed over all timed launches since the last
+ * bxg_batch_reset_counters (sweeps, solves, the run half of optimizer rounds). */
+int bxg_batch_device_ms(bxg_batch* b, double* total_ms);
 /* Launches issued by this batch since creation (kernels of this library). */
 int bxg_batch_launches(bxg_batch* b, int64_t* launches);
 
@@ -322,6 +325,42 @@ int bxg_optimize_reinit(bxg_batch* b, bxg_population* pop, int first_round,
                         double* kappa);
 int bxg_optimize_run(bxg_batch* b, bxg_population* pop, int32_t* status,
                      double* value, int32_t* remaining);
+/* optimize_problem's driver loop (:828-857) over a batch: rounds of
+ * bxg_optimize_round until `time_limit` seconds have passed (<= 0: no limit) or
+ * `max_rounds` rounds are done (<= 0: no limit; one of the two is required).
+ * The deadline also reaches the kernels (stop_task).  `update`, when given, is
+ * called about once a second with what the reference hands ctx.update
+ * (:839-853): remaining constraints, value and loop of the best member, seconds
+ * since the call, restarts so far.  With a communicator the incumbent exchange
+ * runs every `exchange_every` rounds (0: never). */
+typedef void (*bxg_update_fn)(int remaining, double value, int64_t loop,
+                              double duration, int64_t restarts, void* user);
+typedef struct bxg_comm bxg_comm;
+int bxg_optimize(bxg_batch* b, bxg_population* pop, bxg_comm* comm,
+                 double time_limit, int64_t max_rounds, int exchange_every,
+                 bxg_update_fn update, void* user, int64_t* rounds_done);
+/* rounds run on this population; seconds (device clock, from the first round)
+ * until a lane first offered a solution, -1 if none yet */
+int bxg_population_stats(bxg_population* pop, int64_t* rounds,
+                         double* first_solution_seconds);
+
+/* ---- multi-GPU ---------------------------------------------------------------
+ * The optimizer layer shards over workers: every rank owns its
+ * lanes and its copy of the population, built from the same master seed.  The
+ * only exchange is the incumbent: one ncclAllGather of every rank's best member
+ * (scores + vector) on the batch's stream, then each rank adopts the box-wide
+ * best -- fewest remaining constraints, then objective, then lowest rank -- in
+ * place of its worst member unless it already holds it.  No host
+ * synchronisation: the next round queues behind it.  NCCL is bound at run
+ * time (libnccl.so.2).  The reference has no counterpart: its workers share one
+ * address space (best_solution_recorder, :459-594). */
+int bxg_comm_unique_id(void* id128); /* ncclGetUniqueId: rank 0 creates, the caller distributes */
+int bxg_comm_init(const void* id128, int rank, int nranks, int device, bxg_comm** out);
+void bxg_comm_destroy(bxg_comm* c);
+int bxg_comm_info(const bxg_comm* c, int* rank, int* nranks, int64_t* exchanges);
+/* winner_rank may be NULL (then the call does not wait for the device) */
+int bxg_exchange_best(bxg_batch* b, bxg_population* pop, bxg_comm* c, int* winner_rank);
+
 /* bit_array_hash, bit-array.hpp:410-423 */
 uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
 

@@ -323,14 +323,46 @@ class OracleRun(_RunBase):
 _ref = {}
 
 
-def ref_available(fast: bool = False) -> bool:
-    return os.path.exists(os.path.join(HERE, "_ref", "libbxref_fast.so" if fast else "libbxref.so"))
+def _ref_name(fast) -> str:
+    """fast: False = parity build (contract checks on), True = the same without
+    the checks, "o3" = the reference's release flags (speed baseline only)."""
+    return {False: "libbxref.so", True: "libbxref_fast.so", "o3": "libbxref_o3.so"}[fast]
 
 
-def ref(fast: bool = False):
+def ref_available(fast=False) -> bool:
+    if fast == "o3" and not _cpu_has("avx2", "fma", "bmi2"):
+        return False  # built for x86-64-v3
+    return os.path.exists(os.path.join(HERE, "_ref", _ref_name(fast)))
+
+
+def _cpu_has(*flags) -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    have = set(line.split(":", 1)[1].split())
+                    return all(fl in have for fl in flags)
+    except OSError:
+        pass
+    return False
+
+
+def ref_b200():
+    """oracle/_ref/libbxref_b200.so: integration/itm_b200.cpp compiled against the
+    reference's headers (the only harness library that links the engine)."""
+    if "b200" not in _ref:
+        ref(False)
+        lib = C.CDLL(os.path.join(HERE, "_ref", "libbxref_b200.so"))
+        lib.bxref_solve_b200.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, _i8p, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        _ref["b200"] = lib
+    return _ref["b200"]
+
+
+def ref(fast=False):
     if fast in _ref:
         return _ref[fast]
-    path = os.path.join(HERE, "_ref", "libbxref_fast.so" if fast else "libbxref.so")
+    path = os.path.join(HERE, "_ref", _ref_name(fast))
     lib = C.CDLL(path)
     lib.bxref_default_params.argtypes = [C.POINTER(Params)]
     lib.bxref_open.argtypes = [C.c_char_p, C.POINTER(Params)]
@@ -376,8 +408,9 @@ def ref(fast: bool = False):
     lib.bxref_std_uniform_u64.restype = C.c_uint64
     lib.bxref_std_normal.argtypes = [C.c_double, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32)]
     lib.bxref_generate_seed.argtypes = [C.c_uint64, C.c_uint, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
-    lib.bxref_solve_b200.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, _i8p, C.POINTER(C.c_double),
-                                     C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    lib.bxref_open_arrays.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int, C.c_int, _i32p,
+                                      _f64p, C.c_double, C.POINTER(Params)]
+    lib.bxref_open_arrays.restype = C.c_void_p
     lib.bxref_std_pow.argtypes = [C.c_double, C.c_double]
     lib.bxref_std_pow.restype = C.c_double
     lib.bxref_bb_solve.argtypes = [C.c_int, _f64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int]
@@ -418,9 +451,20 @@ def read_opt_trace(lib, prefix, t, m, n, nnz, size):
 class RefProblem:
     """LP file -> reference parser -> merged constraints."""
 
-    def __init__(self, lp_path: str, params: Params, fast: bool = False):
+    def __init__(self, lp_path: str | None, params: Params, fast=False, inst: dict | None = None):
+        """From an LP file (the reference's parser), or from an instance dict
+        (bxref_open_arrays: raw_problem filled directly, for instances whose LP
+        text the reference's parser takes minutes to read)."""
         self.lib = ref(fast)
-        self.h = self.lib.bxref_open(lp_path.encode(), C.byref(params))
+        if inst is not None:
+            i32 = lambda a: np.ascontiguousarray(a, np.int32)
+            self.h = self.lib.bxref_open_arrays(
+                inst["m"], inst["n"], i32(inst["row_ptr"]), i32(inst["col"]), i32(inst["factor"]),
+                i32(inst["cmin"]), i32(inst["cmax"]), int(inst["maximize"]), len(inst["obj_var"]),
+                i32(inst["obj_var"]), np.ascontiguousarray(inst["obj_factor"], np.float64),
+                float(inst["cost_constant"]), C.byref(params))
+        else:
+            self.h = self.lib.bxref_open(lp_path.encode(), C.byref(params))
         if not self.h:
             raise RuntimeError(f"reference could not read {lp_path}")
         v = [C.c_int() for _ in range(5)]
@@ -471,8 +515,8 @@ class RefProblem:
         problem and result types over the engine's C ABI."""
         x = np.zeros(self.n, np.int8)
         value, rem, loop = C.c_double(), C.c_int(), C.c_int64()
-        st = self.lib.bxref_solve_b200(self.h, seed, restarts, device, x, C.byref(value), C.byref(rem),
-                                       C.byref(loop))
+        st = ref_b200().bxref_solve_b200(self.h, seed, restarts, device, x, C.byref(value), C.byref(rem),
+                                         C.byref(loop))
         return {"status": st, "x": x, "value": value.value, "remaining": rem.value, "loop": loop.value}
 
     def solve(self, seed: int):

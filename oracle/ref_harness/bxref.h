@@ -66,6 +66,12 @@ void bxref_default_params(bxref_params* p);
 /* Problem handle: parse LP (reference parser), unpreprocess, clamp parameters
  * (context_set_solver_parameters), make_merged_constraints. */
 void* bxref_open(const char* lp_path, const bxref_params* p);
+/* The same from arrays (merged-constraint form), without the LP parser. */
+void* bxref_open_arrays(int m, int n, const int* row_ptr, const int* col,
+                        const int* factor, const int* cmin, const int* cmax,
+                        int maximize, int n_obj, const int* obj_var,
+                        const double* obj_factor, double cost_constant,
+                        const bxref_params* p);
 void bxref_close(void* h);
 /* problem_type = baryonyx::problem_solver_type value; maximize = 1 if
  * objective_function_type::maximize. */

@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <fstream>
+#include <limits>
+#include <string>
 #include <random>
 
 using namespace baryonyx;
@@ -229,6 +231,80 @@ bxref_open(const char* lp_path, const bxref_params* p)
     for (const auto& c : h->csts)
         h->nnz += length(c.elements);
 
+    return h.release();
+}
+
+// The same handle from arrays: baryonyx::raw_problem filled directly, for
+// instances whose LP text the reference's parser would take minutes to read
+// (its objective look-up is quadratic: parser.cpp:1085-1097; 519 s for the
+// rail4284-shaped file).  Rows: cmin == cmax -> "=", a finite side -> ">=" /
+// "<=", both -> two constraints over the same elements, which
+// make_merged_constraints merges again.  Variables are binary, named x0..x{n-1}.
+void*
+bxref_open_arrays(int m,
+                  int n,
+                  const int* row_ptr,
+                  const int* col,
+                  const int* factor,
+                  const int* cmin,
+                  const int* cmax,
+                  int maximize,
+                  int n_obj,
+                  const int* obj_var,
+                  const double* obj_factor,
+                  double cost_constant,
+                  const bxref_params* p)
+{
+    auto h = std::make_unique<bxref::handle>();
+    {
+        auto ptr = make_context(3);
+        h->orig = to_reference(*p);
+        context_set_solver_parameters(ptr, h->orig);
+        h->ctx.parameters = context_get_solver_parameters(ptr);
+    }
+
+    raw_problem& raw = h->raw;
+    raw.strings = std::make_shared<string_buffer>();
+    raw.type = maximize ? objective_function_type::maximize : objective_function_type::minimize;
+    raw.vars.names.reserve(n);
+    raw.vars.values.reserve(n);
+    for (int i = 0; i != n; ++i) {
+        raw.vars.names.emplace_back(raw.strings->append("x" + std::to_string(i)));
+        raw.vars.values.emplace_back(0, 1, variable_type::binary);
+    }
+    raw.objective.value = cost_constant;
+    for (int i = 0; i != n_obj; ++i)
+        raw.objective.elements.emplace_back(obj_factor[i], obj_var[i]);
+
+    int id = 0;
+    for (int k = 0; k != m; ++k) {
+        auto elements = [&] {
+            std::vector<function_element> e;
+            e.reserve(row_ptr[k + 1] - row_ptr[k]);
+            for (int t = row_ptr[k]; t != row_ptr[k + 1]; ++t)
+                e.emplace_back(factor[t], col[t]);
+            return e;
+        };
+        const auto label = raw.strings->append("c" + std::to_string(k));
+        const bool lo = cmin[k] != std::numeric_limits<int>::min();
+        const bool hi = cmax[k] != std::numeric_limits<int>::max();
+        if (lo && hi && cmin[k] == cmax[k])
+            raw.equal_constraints.emplace_back(label, elements(), cmin[k], id++);
+        else {
+            if (lo)
+                raw.greater_constraints.emplace_back(label, elements(), cmin[k], id++);
+            if (hi)
+                raw.less_constraints.emplace_back(label, elements(), cmax[k], id++);
+        }
+    }
+
+    h->pb = unpreprocess(h->ctx, h->raw);
+    h->csts = itm::make_merged_constraints(h->ctx, h->pb);
+    h->m = length(h->csts);
+    h->n = length(h->pb.vars.values);
+    h->nnz = 0;
+    for (const auto& c : h->csts)
+        h->nnz += length(c.elements);
     return h.release();
 }
 
