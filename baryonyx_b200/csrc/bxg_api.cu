@@ -133,6 +133,7 @@ struct bxg_problem
     std::vector<int> cmin, cmax, bmin, bmax, row_neg, ztype;
     std::vector<int> ex_start, ex_count, ex_flat; // (Z) exhaustive rows: pattern masks
     int max_zrow = 0;
+    int max_amount = 0;
     std::vector<float> row_bytes;
     std::vector<int> obj_var;
     std::vector<double> obj_factor;
@@ -197,6 +198,28 @@ struct bxg_batch
 };
 
 namespace {
+
+__global__ void
+k_globaltimer(unsigned long long* out)
+{
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    *out = now;
+}
+
+// %globaltimer of the device (nanoseconds): what the kernels compare their
+// deadline with (time_limit, stop_task)
+int
+device_clock(cudaStream_t stream, unsigned long long* now)
+{
+    unsigned long long* d_now = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_now), sizeof(unsigned long long), stream));
+    k_globaltimer<<<1, 1, 0, stream>>>(d_now);
+    CUDA_TRY(cudaMemcpyAsync(now, d_now, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaFreeAsync(d_now, stream));
+    return BXG_OK;
+}
 
 int
 fetch_ctl(bxg_batch* b)
@@ -395,6 +418,13 @@ bxg_which_problem_type(int nnz, const int32_t* factor, int has_inequality)
     return has_inequality ? ineq[coefficient] : eq[coefficient];
 }
 
+static int
+problem_create_body(int m, int n, const int32_t* row_ptr, const int32_t* col,
+                    const int32_t* factor, const int32_t* cmin, const int32_t* cmax,
+                    int problem_type, int maximize, int n_obj, const int32_t* obj_var,
+                    const double* obj_factor, double cost_constant, int device,
+                    bxg_problem** out);
+
 int
 bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
                    const int32_t* factor, const int32_t* cmin, const int32_t* cmax,
@@ -402,11 +432,44 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
                    const double* obj_factor, double cost_constant, int device,
                    bxg_problem** out)
 {
+    // no exception crosses the C boundary (the host-side index is built with
+    // std::vector: an allocation failure becomes BXG_E_MEMORY)
+    try {
+        return problem_create_body(m, n, row_ptr, col, factor, cmin, cmax, problem_type, maximize,
+                                   n_obj, obj_var, obj_factor, cost_constant, device, out);
+    } catch (const std::bad_alloc&) {
+        return fail(BXG_E_MEMORY, "bxg_problem_create: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(BXG_E_INVALID, std::string("bxg_problem_create: ") + e.what());
+    } catch (...) {
+        return fail(BXG_E_INVALID, "bxg_problem_create: unexpected failure");
+    }
+}
+
+static int
+problem_create_body(int m, int n, const int32_t* row_ptr, const int32_t* col,
+                    const int32_t* factor, const int32_t* cmin, const int32_t* cmax,
+                    int problem_type, int maximize, int n_obj, const int32_t* obj_var,
+                    const double* obj_factor, double cost_constant, int device,
+                    bxg_problem** out)
+{
     if (!out || m <= 0 || n <= 0 || !row_ptr || !col || !factor || !cmin || !cmax ||
         n_obj < 0 || (n_obj && (!obj_var || !obj_factor)))
         return fail(BXG_E_INVALID, "bxg_problem_create: bad argument");
     if (problem_type < BXG_EQUALITIES_01 || problem_type > BXG_INEQUALITIES_Z)
         return fail(BXG_E_INVALID, "bxg_problem_create: unknown problem type");
+    // the CSR itself, before anything is sized or copied from it
+    if (row_ptr[0] != 0)
+        return fail(BXG_E_INVALID, "bxg_problem_create: row_ptr[0] must be 0");
+    for (int k = 0; k != m; ++k)
+        if (row_ptr[k + 1] <= row_ptr[k])
+            return fail(BXG_E_INVALID, "bxg_problem_create: empty constraint or decreasing row_ptr");
+    for (int e = 0, nnz_ = row_ptr[m]; e != nnz_; ++e) {
+        if (col[e] < 0 || col[e] >= n)
+            return fail(BXG_E_INVALID, "bxg_problem_create: column index out of range");
+        if (factor[e] == 0)
+            return fail(BXG_E_INVALID, "bxg_problem_create: zero factor");
+    }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
@@ -642,6 +705,13 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
 
         if (pb->bmin[k] > pb->bmax[k])
             return fail(BXG_E_UNREALISABLE, "constraint with bound_min > bound_max");
+        // by how much the row's activity (between `lower` and `upper`) can miss its bounds
+        pb->max_amount = std::max(
+          pb->max_amount,
+          static_cast<int>(std::min<long long>(
+            std::max<long long>(static_cast<long long>(pb->bmin[k]) - lower,
+                                static_cast<long long>(upper) - pb->bmax[k]),
+            std::numeric_limits<int>::max())));
 
         if (pb->bmin[k] != pb->bmax[k] && pb->family != FAM_Z &&
             std::min(pb->bmax[k] + (pb->family == FAM_101 ? neg : 0), len) == len)
@@ -764,6 +834,7 @@ bxg_problem_create(int m, int n, const int32_t* row_ptr, const int32_t* col,
     d.row_bytes = pb->d_row_bytes.p;
     d.ztype = pb->d_ztype.p;
     d.max_zrow = pb->max_zrow;
+    d.max_amount = pb->max_amount;
     d.ex_start = pb->family == FAM_Z ? pb->d_ex_start.p : nullptr;
     d.ex_count = pb->family == FAM_Z ? pb->d_ex_count.p : nullptr;
     d.ex_flat = pb->family == FAM_Z ? pb->d_ex_flat.p : nullptr;
@@ -818,6 +889,11 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
                     "the reference when n > m");
     if (p->order == ORDER_CYCLE && pb->n > pb->m)
         return fail(BXG_E_UNSUPPORTED, "cycle reaches pi_sign_change: undefined when n > m");
+    if (p->limit == std::numeric_limits<int64_t>::max() &&
+        !(p->time_limit > 0 && std::isfinite(p->time_limit)) && !(p->kappa_step > 0))
+        return fail(BXG_E_INVALID,
+                    "no limit, no time_limit and kappa_step = 0: a run that cannot end (the reference "
+                    "would spin too); give one of them");
 
     CUDA_TRY(cudaSetDevice(pb->device));
 
@@ -902,7 +978,9 @@ bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** 
     CUDA_TRY(cudaMemset(b->d_ctl.p, 0, sizeof(LaneCtl) * L));
     CUDA_TRY(cudaMemset(b->d_bestx.p, 0, b->d_bestx.bytes()));
 
-    b->cfg = plan_launch(pb->dev, pb->device, n_lanes);
+    b->cfg = plan_launch(pb->dev, pb->device, n_lanes,
+                         p->order == ORDER_INFEASIBILITY_DECR || p->order == ORDER_INFEASIBILITY_INCR ||
+                           p->order == ORDER_CYCLE);
     {
         // the row activities (4 m bytes) and the lane's control blocks always
         // live in shared memory: refuse what cannot fit instead of failing at
@@ -1292,6 +1370,16 @@ bxg_batch_solve(bxg_batch* b, int32_t* status, double* value, int32_t* remaining
         return fail(BXG_E_INVALID, "bxg_batch_solve: call bxg_batch_begin first");
     bxg_problem* pb = b->pb;
     CUDA_TRY(cudaSetDevice(pb->device));
+    if (b->p.time_limit > 0 && std::isfinite(b->p.time_limit)) {
+        // solver_functor's is_timelimit_reached (itm-solver-common.hpp:162,186,210,
+        // 228-232): the lanes test the device clock once per sweep
+        unsigned long long now = 0;
+        int rc_ = device_clock(b->stream, &now);
+        if (rc_ != BXG_OK)
+            return rc_;
+        b->deadline_ns = now + static_cast<unsigned long long>(b->p.time_limit * 1e9);
+    } else
+        b->deadline_ns = 0;
     refresh_params(b);
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     launch_solve(pb->dev, b->prm, b->dev, b->cfg, b->stream);

@@ -113,6 +113,9 @@ struct Lane
     int stage_cap;
     int* oR;
     int2* mo;
+    // the (row, amount) list of the infeasibility orders packed amount << 16 | row
+    // in shared memory when the plan says so (one thread sorts it every sweep)
+    uint32_t* mop;
     LaneCtl* ctl;
     Shared* sh;
     unsigned char* zs; // (Z) scratch of the sub-solvers, global memory
@@ -220,6 +223,16 @@ struct PairLessDecr
 struct PairLessIncr
 {
     __device__ bool operator()(const int2& a, const int2& b) const { return a.y < b.y; }
+};
+
+struct PackedLessDecr
+{
+    __device__ bool operator()(const uint32_t& a, const uint32_t& b) const { return (b >> 16) < (a >> 16); }
+};
+
+struct PackedLessIncr
+{
+    __device__ bool operator()(const uint32_t& a, const uint32_t& b) const { return (a >> 16) < (b >> 16); }
 };
 
 struct PiLessDecr
@@ -1226,6 +1239,7 @@ update_row_z(int k, double kappa, int push, double obj_amp)
 
         const int bkmin = hdr.bmin, bkmax = hdr.bmax;
         int selected;
+        int need_cta = 0; // the branch-and-bound enumeration runs on the whole CTA
         if (zt == Z_LINEAR)
             selected = z_select_prefix(R, r_size, bkmin, bkmax, maximize);
         else {
@@ -1234,13 +1248,38 @@ update_row_z(int k, double kappa, int push, double obj_amp)
             if (zt == Z_UNCONSTRAINED_BRANCH_AND_BOUND || zt == Z_UNCONSTRAINED_EXHAUSTIVE)
                 selected = z_select_prefix(R, r_size, bkmin, bkmax, maximize);
             if (selected == -2) {
-                if (zt == Z_BRANCH_AND_BOUND || zt == Z_UNCONSTRAINED_BRANCH_AND_BOUND)
-                    selected = z_bb_solve(w, R, r_size, maximize, bkmin, bkmax);
-                else
+                if (zt == Z_BRANCH_AND_BOUND || zt == Z_UNCONSTRAINED_BRANCH_AND_BOUND) {
+                    if (r_size <= kZParallelMax) {
+                        int b0 = bkmin, b1 = bkmax;
+                        z_bb_prepare(w, R, r_size, maximize, b0, b1);
+                        sh->redi[0] = b0;
+                        sh->redi[1] = b1;
+                        need_cta = 1;
+                    } else
+                        selected = z_bb_solve(w, R, r_size, maximize, bkmin, bkmax);
+                } else
                     selected = z_ex_solve(w, R, r_size, maximize, pb.ex_flat + pb.ex_start[k],
                                           pb.ex_count[k]);
             }
         }
+        sh->selected = selected;
+        sh->tmp_i = need_cta;
+    }
+    __syncthreads();
+    if (sh->tmp_i) {
+        // (uniform) every thread enumerates its share of the subsets
+        const ZWork w(L.zs, pb.max_zrow);
+        const int b0 = sh->redi[0], b1 = sh->redi[1];
+        __syncthreads(); // redi is the reduction's scratch next
+        const unsigned chosen = z_bb_enumerate(w, r_size, maximize, b0, b1, sh->red, sh->redi);
+        if (tid == 0) {
+            const ZRow R{ L.sk, L.sid, pb.row_a + r0 };
+            sh->selected = z_bb_finish(w, R, r_size, maximize, chosen);
+        }
+    }
+    if (tid == 0) {
+        const ZRow R{ L.sk, L.sid, pb.row_a + r0 };
+        const int selected = sh->selected;
 
         // scalars of local_affect: pi_k moves in all three cases
         const double old_pi = L.pi[k];
@@ -1401,6 +1440,8 @@ violated_scan(Lane& L, int mode)
                 const int pos = count + __popc(mask & ((1u << lane) - 1u));
                 if (mode == 0)
                     L.oR[pos] = k;
+                else if (L.mop)
+                    L.mop[pos] = ((uint32_t)amount << 16) | (uint32_t)k;
                 else
                     L.mo[pos] = make_int2(k, amount);
             }
@@ -1458,10 +1499,16 @@ order_prepare(Lane& L, int order, int oR_len, int mo_len)
         seq_shuffle(Plain<int>{ L.oR }, 0, oR_len, rng);
         break;
     case ORDER_INFEASIBILITY_DECR:
-        seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessDecr());
+        if (L.mop)
+            seq_std_sort(Plain<uint32_t>{ L.mop }, mo_len, PackedLessDecr());
+        else
+            seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessDecr());
         break;
     case ORDER_INFEASIBILITY_INCR:
-        seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessIncr());
+        if (L.mop)
+            seq_std_sort(Plain<uint32_t>{ L.mop }, mo_len, PackedLessIncr());
+        else
+            seq_std_sort(Plain<int2>{ L.mo }, mo_len, PairLessIncr());
         break;
     case ORDER_LAGRANGIAN_DECR:
         seq_std_sort(Plain<int>{ L.oR }, oR_len, PiLessDecr{ L.pi });
@@ -1523,10 +1570,10 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     for (int i = 0; i < len; ++i) {
         int k;
         if (pairs)
-            k = L.mo[i].x;
+            k = L.mop ? (int)(L.mop[i] & 0xffffu) : L.mo[i].x;
         else
             k = L.oR[order == ORDER_REVERSING ? len - 1 - i : i];
-        const int k_next = i + 1 < len ? (pairs ? L.mo[i + 1].x
+        const int k_next = i + 1 < len ? (pairs ? (L.mop ? (int)(L.mop[i + 1] & 0xffffu) : L.mo[i + 1].x)
                                                 : L.oR[order == ORDER_REVERSING ? len - 2 - i : i + 1])
                                        : -1;
 #if BXG_FAM == 2
@@ -1604,7 +1651,7 @@ objective(Lane& L)
 // ---------------------------------------------------------------------------
 struct SmemPlan
 {
-    int pi_in_smem, x_in_smem, r_in_smem;
+    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem;
     int sort_cap;
     int stage_cap;
 };
@@ -1681,9 +1728,29 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
             s_x[i] = g_x[i];
     }
 
+    // (Z) items / node stack / subvector pool of the sub-solvers: one thread
+    // walks them node by node, so they belong in shared memory when they fit
+    unsigned char* s_zs = nullptr;
+    if (plan.z_in_smem) {
+        off = (off + 15) & ~size_t(15);
+        s_zs = smem + off;
+        off += b.z_bytes;
+    }
+
+    uint32_t* s_mop = nullptr;
+    if (plan.mo_in_smem) {
+        s_mop = reinterpret_cast<uint32_t*>(smem + off);
+        off += sizeof(uint32_t) * (size_t)(pb.m + 1);
+        const int2* g_mo = b.mo + (size_t)lane_id * b.order_cap;
+        const int n_mo = min(ctl->mo_len, pb.m);
+        for (int i = tid; i < n_mo; i += T)
+            s_mop[i] = ((uint32_t)g_mo[i].y << 16) | (uint32_t)g_mo[i].x;
+    }
+
     if (tid == 0) {
         L.pb = &pb;
         L.pr = &pr;
+        L.mop = s_mop;
         L.row_hdr = pb.row_hdr;
         L.row_info = pb.row_info;
         L.row_eptr = pb.row_eptr;
@@ -1702,7 +1769,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.sh = sh;
         L.P = b.P + (size_t)lane_id * pb.nnz;
         L.ctl = ctl;
-        L.zs = b.z_scratch ? b.z_scratch + (size_t)lane_id * b.z_bytes : nullptr;
+        L.zs = s_zs ? s_zs : (b.z_scratch ? b.z_scratch + (size_t)lane_id * b.z_bytes : nullptr);
         L.oR = b.oR + (size_t)lane_id * b.order_cap;
         L.mo = b.mo + (size_t)lane_id * b.order_cap;
         L.sort_cap = plan.sort_cap; // (the CTA-wide sort also runs on a scratch in global memory)
@@ -1789,6 +1856,12 @@ lane_close(Lane& L, Lists& ls, const DevProblem& pb, const DevBatch& b,
         int* g_act = b.act + (size_t)lane_id * pb.m;
         for (int i = tid; i < pb.m; i += T)
             g_act[i] = L.act[i];
+    }
+    if (plan.mo_in_smem) {
+        int2* g_mo = b.mo + (size_t)lane_id * b.order_cap;
+        const int n_mo = min(ls.mo_len, pb.m);
+        for (int i = tid; i < n_mo; i += T)
+            g_mo[i] = make_int2((int)(L.mop[i] & 0xffffu), (int)(L.mop[i] >> 16));
     }
     if (tid == 0) {
         L.ctl->rng = L.sh->rng;
@@ -2339,8 +2412,11 @@ pow2_at_least(int v)
     return p;
 }
 
+size_t z_scratch_bytes(int max_zrow);
+
 static size_t
-smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, int stage_cap)
+smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, int stage_cap, int mo_in = 0,
+           int z_in = 0)
 {
     size_t off = kLaneBytes + align16(sizeof(Shared));
     if (r_in) {
@@ -2353,6 +2429,10 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, in
     off += sizeof(int) * (size_t)pb.m;
     if (x_in)
         off += sizeof(uint32_t) * (size_t)pb.xw32;
+    if (z_in)
+        off += 16 + z_scratch_bytes(pb.max_zrow);
+    if (mo_in)
+        off += sizeof(uint32_t) * (size_t)(pb.m + 1);
     return off + 16;
 }
 
@@ -2380,7 +2460,7 @@ cta_class_blocks(int threads)
 }
 
 LaunchCfg
-plan_launch(const DevProblem& pb, int device, int n_lanes)
+plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order)
 {
     int max_optin = 0, per_sm = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -2395,6 +2475,10 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     cfg.r_in_smem = 1;
     cfg.pi_in_smem = 1;
     cfg.x_in_smem = 1;
+    // the sorted (row, amount) list of the infeasibility orders: packed in shared
+    // memory when rows and amounts fit 16 bits each
+    cfg.mo_in_smem = pairs_order && pb.m <= 0xffff && pb.max_amount <= 0xffff;
+    cfg.z_in_smem = pb.max_zrow > 0 && z_scratch_bytes(pb.max_zrow) <= 8192;
     cfg.sort_cap = pow2_at_least(pb.max_row);
     // staging buffer of the reduced-cost gather: at least one column, at most
     // the longest row's entries
@@ -2403,10 +2487,12 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     cfg.stage_cap = stage_min;
     auto bytes = [&]() {
         return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap,
-                          cfg.stage_cap);
+                          cfg.stage_cap, cfg.mo_in_smem, cfg.z_in_smem);
     };
     // with the smallest staging buffer, drop the largest consumers first until
     // the plan fits
+    if (bytes() > budget)
+        cfg.mo_in_smem = 0;
     if (bytes() > budget)
         cfg.x_in_smem = 0;
     if (bytes() > budget) {
@@ -2440,6 +2526,9 @@ plan_launch(const DevProblem& pb, int device, int n_lanes)
     int t = ((pb.p95_row + 31) / 32) * 32;
     if (t < 64)
         t = 64;
+    // branch-and-bound rows are enumerated by the whole CTA (z_bb_enumerate)
+    if (pb.max_zrow >= 10 && t < 128)
+        t = 128;
     if (t > 1024)
         t = 1024;
     int sms = 0;
@@ -2516,7 +2605,7 @@ BXG_FAM_FN(launch_begin)(const DevProblem& pb, const DevParams& pr, const DevBat
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
                init_on_device, init_random, d_cost_orig, plan);
 }
@@ -2525,7 +2614,7 @@ void
 BXG_FAM_FN(launch_order_init)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
 }
 
@@ -2533,7 +2622,7 @@ void
 BXG_FAM_FN(launch_sweep)(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
 }
 
@@ -2541,7 +2630,7 @@ void
 BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s, int optimizer)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan, optimizer);
 }
 
@@ -2549,7 +2638,7 @@ void
 BXG_FAM_FN(launch_optimize)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                 const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_optimize, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
@@ -2557,7 +2646,7 @@ void
 BXG_FAM_FN(launch_objective)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 

@@ -64,6 +64,7 @@ struct DevProblem
     int need_z;
     int tail_rows; // rows whose select_variables scan can read R[r_size]
     int max_zrow;  // (Z) longest row handled by branch-and-bound / exhaustive
+    int max_amount; // largest amount by which a row can be violated
     double cost_constant;
 
     const RowHdr* row_hdr; // [m]
@@ -210,12 +211,12 @@ struct LaunchCfg
 {
     int threads;
     size_t smem;
-    int pi_in_smem, x_in_smem, r_in_smem;
+    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem;
     int sort_cap;
     int stage_cap;
 };
 
-LaunchCfg plan_launch(const DevProblem& pb, int device, int n_lanes);
+LaunchCfg plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order);
 size_t lane_scratch_bytes(const DevProblem& pb, const LaunchCfg& cfg);
 size_t z_scratch_bytes(int max_zrow);
 

@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <memory>
 #include <fstream>
 #include <string_view>
 #include <unordered_map>
@@ -496,6 +498,8 @@ lp_parse(std::string text, bxg_lp& out)
         t.pop(2); // objective label
 
     while (!lp::is_keyword(t.at(0))) {
+        if (t.at(0).empty())
+            return "bad_objective";
         if (t.at(0) == "[" || ((t.at(0) == "+" || t.at(0) == "-") && t.at(1) == "["))
             return "quadratic objective (outside this engine)";
         const lp::element e = lp::read_element(t);
@@ -572,6 +576,8 @@ lp_parse(std::string text, bxg_lp& out)
     if (lp::same_word(t.at(0), "bounds") || lp::same_word(t.at(0), "bound")) {
         t.pop(lp::same_word(t.at(1), ":") ? 2 : 1);
         while (!lp::is_keyword(t.at(0))) {
+            if (t.at(0).empty())
+                return "bad_bound";
             double lo = 0.0, hi = std::numeric_limits<double>::infinity();
             std::string_view name;
             int used = 0;
@@ -652,6 +658,10 @@ lp_parse(std::string text, bxg_lp& out)
     if (lp::same_word(t.at(0), "binary") || lp::same_word(t.at(0), "binaries") || lp::same_word(t.at(0), "bin")) {
         t.pop(lp::same_word(t.at(1), ":") ? 2 : 1);
         while (!lp::is_keyword(t.at(0))) {
+            // (truncated text: the reference's loop would not end here either; a
+            // library entry point reports it instead)
+            if (t.at(0).empty())
+                return "bad_binary";
             const int id = known(t.at(0));
             if (id < 0)
                 return "bad_binary";
@@ -664,6 +674,8 @@ lp_parse(std::string text, bxg_lp& out)
     if (lp::same_word(t.at(0), "general") || lp::same_word(t.at(0), "generals") || lp::same_word(t.at(0), "gen")) {
         t.pop(lp::same_word(t.at(1), ":") ? 2 : 1);
         while (!lp::is_keyword(t.at(0))) {
+            if (t.at(0).empty())
+                return "bad_general";
             const int id = known(t.at(0));
             if (id < 0)
                 return "bad_general";
@@ -834,7 +846,16 @@ bxg_lp_parse(const char* text, size_t length, int pre_order, bxg_lp** out)
 {
     if (!text || !out)
         return fail(BXG_E_INVALID, "bxg_lp_parse: bad argument");
-    return lp_build(std::string(text, length), pre_order, out);
+    // no exception crosses the C boundary
+    try {
+        return lp_build(std::string(text, length), pre_order, out);
+    } catch (const std::bad_alloc&) {
+        return fail(BXG_E_MEMORY, "LP text: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(BXG_E_INVALID, std::string("LP text: ") + e.what());
+    } catch (...) {
+        return fail(BXG_E_INVALID, "LP text: unexpected failure");
+    }
 }
 
 int
@@ -842,23 +863,33 @@ bxg_lp_read(const char* path, int pre_order, bxg_lp** out)
 {
     if (!path || !out)
         return fail(BXG_E_INVALID, "bxg_lp_read: bad argument");
-    std::FILE* f = std::fopen(path, "rb");
-    if (!f)
-        return fail(BXG_E_INVALID, std::string("LP text: file_not_found: ") + path);
-    std::string text;
-    char chunk[1 << 16];
-    if (std::fseek(f, 0, SEEK_END) == 0) { // one read when the size is known
-        const long size = std::ftell(f);
-        std::rewind(f);
-        if (size > 0) {
-            text.resize(static_cast<size_t>(size));
-            text.resize(std::fread(&text[0], 1, text.size(), f));
+    struct closer
+    {
+        void operator()(std::FILE* f) const { std::fclose(f); }
+    };
+    try {
+        std::unique_ptr<std::FILE, closer> f(std::fopen(path, "rb"));
+        if (!f)
+            return fail(BXG_E_INVALID, std::string("LP text: file_not_found: ") + path);
+        struct stat st;
+        if (fstat(fileno(f.get()), &st) != 0 || S_ISDIR(st.st_mode))
+            return fail(BXG_E_INVALID, std::string("LP text: not a readable file: ") + path);
+        std::string text;
+        if (S_ISREG(st.st_mode) && st.st_size > 0) { // one read when the size is known
+            text.resize(static_cast<size_t>(st.st_size));
+            text.resize(std::fread(&text[0], 1, text.size(), f.get()));
         }
+        char chunk[1 << 16];
+        for (size_t got; (got = std::fread(chunk, 1, sizeof chunk, f.get())) > 0;) // pipes, files that grew
+            text.append(chunk, got);
+        return lp_build(std::move(text), pre_order, out);
+    } catch (const std::bad_alloc&) {
+        return fail(BXG_E_MEMORY, "LP text: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(BXG_E_INVALID, std::string("LP text: ") + e.what());
+    } catch (...) {
+        return fail(BXG_E_INVALID, "LP text: unexpected failure");
     }
-    for (size_t got; (got = std::fread(chunk, 1, sizeof chunk, f)) > 0;) // pipes, files that grew
-        text.append(chunk, got);
-    std::fclose(f);
-    return lp_build(std::move(text), pre_order, out);
 }
 
 void

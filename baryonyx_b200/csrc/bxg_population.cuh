@@ -270,14 +270,6 @@ k_pop_replace(const __grid_constant__ DevProblem pb, const __grid_constant__ Dev
         dst[w] = src[w];
 }
 
-__global__ void
-k_globaltimer(unsigned long long* out)
-{
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    *out = now;
-}
-
 using engine_t = std::default_random_engine;
 
 uint32_t
@@ -1058,13 +1050,9 @@ bxg_optimize_reinit(bxg_batch* b, bxg_population* pop, int first_round, double* 
     }
     if (!pop->t0_ns) {
         // the device clock the durations count from (m_start, :467-480)
-        unsigned long long* d_now = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_now), sizeof(unsigned long long), b->stream));
-        k_globaltimer<<<1, 1, 0, b->stream>>>(d_now);
-        CUDA_TRY(cudaMemcpyAsync(&pop->t0_ns, d_now, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                 b->stream));
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
-        CUDA_TRY(cudaFreeAsync(d_now, b->stream));
+        int rc_ = device_clock(b->stream, &pop->t0_ns);
+        if (rc_ != BXG_OK)
+            return rc_;
     }
 
     if (first_round) {
@@ -1221,12 +1209,9 @@ bxg_optimize(bxg_batch* b, bxg_population* pop, bxg_comm* comm, double time_limi
         // stop_task for the kernels: the lanes leave their loops at the first
         // sweep boundary past the deadline (device clock)
         unsigned long long now = 0;
-        unsigned long long* d_now = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_now), sizeof(unsigned long long), b->stream));
-        k_globaltimer<<<1, 1, 0, b->stream>>>(d_now);
-        CUDA_TRY(cudaMemcpyAsync(&now, d_now, sizeof(now), cudaMemcpyDeviceToHost, b->stream));
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
-        CUDA_TRY(cudaFreeAsync(d_now, b->stream));
+        int rc_ = device_clock(b->stream, &now);
+        if (rc_ != BXG_OK)
+            return rc_;
         b->deadline_ns = now + static_cast<unsigned long long>(time_limit * 1e9);
     }
 

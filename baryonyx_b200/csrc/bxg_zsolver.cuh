@@ -312,6 +312,178 @@ z_bb_solve(const ZWork& w, const ZRow& R, int r_size, bool maximize, int b_min, 
     return z_finish(w, R, r_size, maximize);
 }
 
+// ---------------------------------------------------------------------------
+// branch_and_bound_solver::solve by the whole CTA.
+//
+// The reference's search (branch-and-bound-solver.hpp:396-448) is a depth-first
+// enumeration cut only by the factor sum, so what it returns is a closed form:
+// let C be the subsets other than {} and {first item} whose factor sum is inside
+// the bounds and whose reduced-cost sum z strictly beats the initial bound
+// (+-infinity).  If C is not empty the answer is the member of C with the best
+// z, and among equal z the one the search meets first: subsets are met in
+// lexicographic order of their increasing index sequences, a prefix before its
+// extensions.  If C is empty the answer is {first item} when that is inside,
+// else {} (the two nodes the search starts from are stored without being
+// compared).  An equality row whose adjusted bound is 0 returns {} at once.
+// z is accumulated over the chosen items in increasing index, as the search
+// accumulates it down a branch, so every sum has the reference's bits.
+//
+// Here every thread owns one pattern of the first q items and walks all
+// patterns of the others; a block reduction picks the winner.
+// ---------------------------------------------------------------------------
+constexpr int kZParallelMax = 20; // rows up to this length (2^20 subsets); longer ones stay sequential
+
+// sorted items, positive factors, adjusted bounds: z_bb_prepare
+__device__ inline void
+z_bb_prepare(const ZWork& w, const ZRow& R, int r_size, bool maximize, int& b_min, int& b_max)
+{
+    for (int i = 0; i != r_size; ++i) {
+        ZItem it;
+        it.r = R.value(i);
+        it.sum_z = 0.0;
+        it.variable = R.sid[i];
+        it.original_factor = R.factor(i);
+        it.factor = it.original_factor < 0 ? -it.original_factor : it.original_factor;
+        it.result = 0;
+        w.items[i] = it;
+    }
+    seq_std_sort(Plain<ZItem>{ w.items }, r_size, ZRatioLess{ maximize });
+    for (int i = 0; i != r_size; ++i) {
+        if (w.items[i].original_factor < 0) {
+            b_min += w.items[i].factor;
+            b_max += w.items[i].factor;
+        }
+    }
+}
+
+// A is met before B by the depth-first search (A != B)
+__device__ __forceinline__ bool
+z_met_first(unsigned A, unsigned B)
+{
+    const int j = __ffs((int)(A ^ B)) - 1;
+    return ((A >> j) & 1u) ? ((B >> (j + 1)) != 0u) : ((A >> (j + 1)) == 0u);
+}
+
+// All threads.  red_z / red_m: shared scratch of 32 entries each.  Returns the
+// chosen subset as a bit mask over the sorted items (uniform).
+__device__ inline unsigned
+z_bb_enumerate(const ZWork& w, int r_size, bool maximize, int b_min, int b_max, double* red_z,
+               int* red_m)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    const bool equality = b_min == b_max;
+    const double bad = maximize ? -CUDART_INF : CUDART_INF;
+    auto inside = [&](int s) { return equality ? s == b_min : (b_min <= s && s <= b_max); };
+    auto better = [&](double z, unsigned m, double bz, unsigned bm) {
+        if (bm == 0xffffffffu)
+            return true;
+        if (z != bz)
+            return maximize ? z > bz : z < bz;
+        return z_met_first(m, bm);
+    };
+
+    double bz = bad;
+    unsigned bm = 0xffffffffu; // none
+    if (!(equality && b_min == 0)) {
+        int q = 0;
+        while ((2 << q) <= T && q + 1 <= r_size)
+            ++q;
+        const unsigned lo = (unsigned)tid;
+        if (lo < (1u << q)) {
+            int sf0 = 0;
+            double z0 = 0.0;
+            for (int i = 0; i < q; ++i)
+                if ((lo >> i) & 1u) {
+                    sf0 += w.items[i].factor;
+                    z0 = __dadd_rn(z0, w.items[i].r);
+                }
+            // the other items in three groups, lowest indices outermost: a group's
+            // partial sums are shared by everything nested below it, and an
+            // inequality row drops a whole nest once the factor sum is past b_max
+            const int nb = r_size - q;
+            const int n1 = nb / 3, n2 = nb / 3, n3 = nb - n1 - n2;
+            const int i1 = q, i2 = q + n1, i3 = q + n1 + n2;
+            auto add_group = [&](unsigned pat, int first, int& sf, double& z) {
+                for (unsigned rest = pat, i = (unsigned)first; rest; rest >>= 1, ++i)
+                    if (rest & 1u) {
+                        sf += w.items[i].factor;
+                        z = __dadd_rn(z, w.items[i].r);
+                    }
+            };
+            // (factors are positive here: a sum past b_max never comes back inside,
+            // for an equality row as well)
+            if (sf0 <= b_max) {
+                for (unsigned p1 = 0; p1 < (1u << n1); ++p1) {
+                    int sf1 = sf0;
+                    double z1 = z0;
+                    add_group(p1, i1, sf1, z1);
+                    if (sf1 > b_max)
+                        continue;
+                    for (unsigned p2 = 0; p2 < (1u << n2); ++p2) {
+                        int sf2 = sf1;
+                        double z2 = z1;
+                        add_group(p2, i2, sf2, z2);
+                        if (sf2 > b_max)
+                            continue;
+                        for (unsigned p3 = 0; p3 < (1u << n3); ++p3) {
+                            const unsigned m = lo | (p1 << i1) | (p2 << i2) | (p3 << i3);
+                            if (m < 2u)
+                                continue; // {} and {first item}: the fallbacks
+                            int sf = sf2;
+                            double z = z2;
+                            add_group(p3, i3, sf, z);
+                            if (inside(sf) && (maximize ? z > bad : z < bad) && better(z, m, bz, bm)) {
+                                bz = z;
+                                bm = m;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // block reduction with the same order
+    for (int o = 16; o; o >>= 1) {
+        const double oz = __shfl_xor_sync(0xffffffffu, bz, o);
+        const unsigned om = __shfl_xor_sync(0xffffffffu, bm, o);
+        if (om != 0xffffffffu && better(oz, om, bz, bm)) {
+            bz = oz;
+            bm = om;
+        }
+    }
+    if (ln == 0) {
+        red_z[wp] = bz;
+        red_m[wp] = (int)bm;
+    }
+    __syncthreads();
+    bz = red_z[0];
+    bm = (unsigned)red_m[0];
+    for (int v = 1; v < nw; ++v) {
+        const double oz = red_z[v];
+        const unsigned om = (unsigned)red_m[v];
+        if (om != 0xffffffffu && better(oz, om, bz, bm)) {
+            bz = oz;
+            bm = om;
+        }
+    }
+    if (bm == 0xffffffffu) // nothing met in the loop: the two start nodes
+        bm = (!(equality && b_min == 0) && inside(w.items[0].factor)) ? 1u : 0u;
+    return bm;
+}
+
+// tail of branch_and_bound_solver::solve (:489-533) from the chosen subset
+__device__ inline int
+z_bb_finish(const ZWork& w, const ZRow& R, int r_size, bool maximize, unsigned chosen)
+{
+    for (int i = 0; i != r_size; ++i) {
+        const int bit = (chosen >> i) & 1u;
+        w.items[i].result = w.items[i].original_factor > 0 ? bit : 1 - bit;
+    }
+    return z_finish(w, R, r_size, maximize);
+}
+
 } // namespace bxg
+
 
 #endif

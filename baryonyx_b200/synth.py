@@ -134,7 +134,7 @@ def csplib022(m=30, n=50000, lo=5, hi=15, neg_frac=0.2, seed=3, name="csplib022-
     return _finish(m, n, rows, factors, b, b, costs, name=name)
 
 
-def telebus(m=1500, n=7000, seed=4, linear_hi=25, name="telebus-shaped"):
+def telebus(m=1500, n=7000, seed=4, linear_hi=25, name="telebus-shaped", ex_frac=0.05, bb_frac=0.05):
     """C4: general integer coefficients (inequalities_Z).  Most rows are 0/1 or
     +-1 (linear sub-solver); about 10% carry a coefficient with |f| >= 2 drawn
     from U{-3..9}\\{0}: half of those short (< 10 elements, exhaustive), half
@@ -143,10 +143,10 @@ def telebus(m=1500, n=7000, seed=4, linear_hi=25, name="telebus-shaped"):
     rows, factors, cmin, cmax = [], [], [], []
     for k in range(m):
         u = rng.rand()
-        if u < 0.05:
+        if u < ex_frac:
             size = int(rng.randint(3, 10))
             zrow = True
-        elif u < 0.10:
+        elif u < ex_frac + bb_frac:
             size = int(rng.randint(10, 17))
             zrow = True
         else:

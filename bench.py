@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--exchange-every", type=int, default=1, help="incumbent exchange every this many rounds (N>1)")
     ap.add_argument("--seed", type=int, default=42, help="solver_parameters.seed of the optimizer")
     ap.add_argument("--cpu-seconds", type=float, default=0.0, help="time_limit of one reference optimizer run")
+    ap.add_argument("--cpu-builds", default="both", choices=["both", "o2", "o3"],
+                    help="which builds of the reference to time (the faster is quoted)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-lanes", type=int, default=0, help="restarts in the CPU sample (0 = 2 x cores)")
@@ -98,6 +100,8 @@ def bench_params(args, mod):
     """solver_parameters of the bench: the reference's defaults except `limit`."""
     p = mod.default_params()
     p.limit = args.limit
+    if args.workload == "telebus":
+        p.order = 3  # infeasibility_decr: BASELINE configs[3] names the infeasibility ordering
     return mod.clamp_params(p)
 
 
@@ -210,6 +214,8 @@ def cpu_solve_sample(inst, args, n_lanes, seed0):
         kind = "reference"
         p = po.default_params()
         p.limit = args.limit
+        if args.workload == "telebus":
+            p.order = 3
         fd, path = tempfile.mkstemp(suffix=".lp", prefix="bx_bench_")
         os.close(fd)
         synth.write_lp(inst, path)
@@ -514,7 +520,10 @@ def cpu_optimize_sample(inst, args, seconds, seed):
     cores = os.cpu_count() or 1
     p = po.default_params()
     p.limit = args.limit
-    flavours = [f for f in (True, "o3") if po.ref_available(f)]
+    if args.workload == "telebus":
+        p.order = 3
+    wanted = {"both": (True, "o3"), "o2": (True,), "o3": ("o3",)}[args.cpu_builds]
+    flavours = [f for f in wanted if po.ref_available(f)] or [f for f in (True, "o3") if po.ref_available(f)]
     if not flavours:
         raise SystemExit("bench.py: oracle/_ref is not built (python -c 'import __graft_entry__ as g; g.build()')")
     runs = []
@@ -542,7 +551,7 @@ def run_reference_optimize(args):
     seconds = args.cpu_seconds or 8.0
     for w in range(min(args.warmup, 1)):
         cpu_optimize_sample(inst, args, 2.0, args.seed)
-    upd = swp = 0
+    upd = swp = rst = 0
     sec = 0.0
     best = None
     r = None
@@ -550,6 +559,7 @@ def run_reference_optimize(args):
         r = cpu_optimize_sample(inst, args, seconds, args.seed + s)
         upd += r["updates"]
         swp += r["sweeps"]
+        rst += r.get("restarts", 0)
         sec += r["seconds"]
         best = r
     value = upd / sec
@@ -562,7 +572,8 @@ def run_reference_optimize(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config_of(args, wname, inst),
-        "sweeps_per_s": swp / sec,
+        "sweeps_per_s": swp / sec, "restarts_per_s": rst / sec,
+        "time_to_feasible_s": best.get("first_feasible_s"),
         "best": {"remaining": best["remaining"], "value": best["value"] if best["remaining"] == 0 else None},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference",
                          "sample": sample},
@@ -757,6 +768,7 @@ def run_engine_optimize(args):
                 "value": r["rate"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
                 "sample": f"optimize_problem for {r['seconds']:.1f} s on {r['threads']} host threads, {r['flavour']}"
                           + (f"; the other build: {r['other']['rate']:.3g} updates/s" if r.get("other") else ""),
+                "restarts_per_s": r.get("restarts", 0) / r["seconds"], "time_to_feasible_s": r.get("first_feasible_s"),
             }
         print(json.dumps(line), flush=True)
 

@@ -1,5 +1,5 @@
 // itm_b200.cpp -- the file a maintainer adds to the reference (lib/src/) to
-// run baryonyx::solve on the B200 engine: it sees the reference's own types
+// run baryonyx::solve and baryonyx::optimize on the B200 engine: it sees the reference's own types
 // (context, problem, merged_constraint, result) on one side and only
 // include/bxg.h on the other.  Compiled in this repository by oracle/Makefile
 // (as part of the reference harness) so that tests/test_gpu_integration.py can
@@ -13,6 +13,7 @@
 
 #include <bxg.h>
 
+#include <chrono>
 #include <vector>
 
 namespace baryonyx {
@@ -65,6 +66,44 @@ to_pod(const solver_parameters& p)
     return q;
 }
 
+// The merged constraints and the objective as the arrays bxg_problem_create
+// takes; failures of the engine become the reference's solver_failure.
+static bxg_problem*
+make_engine_problem(const problem& pb, const std::vector<merged_constraint>& csts, int device)
+{
+    std::vector<int32_t> row_ptr{ 0 }, col, fac, cmin, cmax;
+    for (const auto& c : csts) {
+        for (const auto& e : c.elements) {
+            col.push_back(e.variable_index);
+            fac.push_back(e.factor);
+        }
+        row_ptr.push_back(static_cast<int32_t>(col.size()));
+        cmin.push_back(c.min);
+        cmax.push_back(c.max);
+    }
+    std::vector<int32_t> ov;
+    std::vector<double> of;
+    for (const auto& e : pb.objective.elements) {
+        ov.push_back(e.variable_index);
+        of.push_back(e.factor);
+    }
+
+    bxg_problem* P = nullptr;
+    const int rc = bxg_problem_create(length(csts), length(pb.vars.values), row_ptr.data(), col.data(),
+                                      fac.data(), cmin.data(), cmax.data(),
+                                      static_cast<int>(pb.problem_type),
+                                      pb.type == objective_function_type::maximize,
+                                      static_cast<int>(ov.size()), ov.data(), of.data(),
+                                      pb.objective.value, device, &P);
+    if (rc == BXG_E_UNREALISABLE)
+        throw solver_failure(solver_error_tag::unrealisable_constraint);
+    if (rc == BXG_E_MEMORY)
+        throw solver_failure(solver_error_tag::not_enough_memory);
+    if (rc != BXG_OK)
+        throw solver_failure(solver_error_tag::no_solver_available);
+    return P;
+}
+
 // What itm::solve (itm.hpp:94-145) calls instead of solve_equalities_01 & co.
 // when a device is present: `restarts` lanes, lane 0 on the context's seed (so
 // one lane returns what solve_problem<...> returns), the best lane wins.
@@ -82,33 +121,8 @@ solve_b200(const context& ctx, const problem& pb, int restarts, int device)
         r.solutions.resize(1);
         r.solutions.back().value = pb.objective.value;
     } else {
-        std::vector<int32_t> row_ptr{ 0 }, col, fac, cmin, cmax;
-        for (const auto& c : csts) {
-            for (const auto& e : c.elements) {
-                col.push_back(e.variable_index);
-                fac.push_back(e.factor);
-            }
-            row_ptr.push_back(static_cast<int32_t>(col.size()));
-            cmin.push_back(c.min);
-            cmax.push_back(c.max);
-        }
-        std::vector<int32_t> ov;
-        std::vector<double> of;
-        for (const auto& e : pb.objective.elements) {
-            ov.push_back(e.variable_index);
-            of.push_back(e.factor);
-        }
-
-        bxg_problem* P = nullptr;
-        int rc = bxg_problem_create(length(csts), variables, row_ptr.data(), col.data(), fac.data(),
-                                    cmin.data(), cmax.data(), static_cast<int>(pb.problem_type),
-                                    pb.type == objective_function_type::maximize,
-                                    static_cast<int>(ov.size()), ov.data(), of.data(),
-                                    pb.objective.value, device, &P);
-        if (rc == BXG_E_UNREALISABLE)
-            throw solver_failure(solver_error_tag::unrealisable_constraint);
-        if (rc != BXG_OK)
-            throw solver_failure(solver_error_tag::no_solver_available);
+        bxg_problem* P = make_engine_problem(pb, csts, device);
+        int rc = BXG_OK;
 
         const bxg_params p = to_pod(ctx.parameters);
         bxg_batch* B = nullptr;
@@ -154,6 +168,149 @@ solve_b200(const context& ctx, const problem& pb, int restarts, int device)
     r.affected_vars = pb.affected_vars;
     r.variables = variables;
     r.constraints = length(csts);
+    return r;
+}
+
+
+// What itm::optimize (itm.hpp:156-203) calls instead of optimize_equalities_01 &
+// co.: optimize_problem<...> (itm-optimizer-common.hpp:778-908) over the engine.
+// `workers` lanes play the reference's threads (0: as many as make the device
+// busy); the population, the workers' seeds (generate_seed on the master engine),
+// the once-a-second ctx.update report, the time limit and the shape of the result
+// (storage_type one / bound / five) are the reference's.  max_rounds > 0 bounds
+// the run by restarts per worker instead of by time (tests).
+static void
+member_to_solution(bxg_population* pop, int i, int variables, solution& s, int* remaining,
+                   long int* loop)
+{
+    std::vector<uint64_t> words(static_cast<size_t>(variables) / 64 + 1);
+    double value = 0;
+    int rem = 0;
+    int64_t lp = 0;
+    if (bxg_population_member(pop, i, words.data(), &value, &rem, nullptr, &lp) != BXG_OK)
+        throw solver_failure(solver_error_tag::no_solver_available);
+    s.value = value;
+    s.variables.resize(variables);
+    for (int v = 0; v != variables; ++v) // convert(), itm-common.hpp (raw_result -> solution)
+        s.variables[v] = static_cast<var_value>((words[v >> 6] >> (v & 63)) & 1u);
+    if (remaining)
+        *remaining = rem;
+    if (loop)
+        *loop = static_cast<long int>(lp);
+}
+
+result
+optimize_b200(const context& ctx, const problem& pb, int workers, int device, long int max_rounds = 0)
+{
+    result r;
+
+    if (ctx.start)
+        ctx.start(ctx.parameters);
+
+    const auto variables = length(pb.vars.values);
+    auto csts = make_merged_constraints(ctx, pb);
+    if (csts.empty() || pb.vars.values.empty()) {
+        r.status = result_status::success;
+        r.solutions.resize(1);
+        r.solutions.back().value = pb.objective.value;
+        r.strings = pb.strings;
+        r.affected_vars = pb.affected_vars;
+        r.variable_name = pb.vars.names;
+        return r;
+    }
+
+    if (workers <= 0)
+        workers = 1024;
+    bxg_problem* P = make_engine_problem(pb, csts, device);
+    const bxg_params p = to_pod(ctx.parameters);
+    bxg_batch* B = nullptr;
+    bxg_population* pop = nullptr;
+    auto release = [&] {
+        bxg_population_destroy(pop);
+        bxg_batch_destroy(B);
+        bxg_problem_destroy(P);
+    };
+    if (bxg_batch_create(P, workers, &p, &B) != BXG_OK ||
+        bxg_population_create(P, &p, init_random_generator_seed(ctx), workers, &pop) != BXG_OK) {
+        release();
+        throw solver_failure(solver_error_tag::not_enough_memory);
+    }
+    std::vector<uint64_t> seeds(workers); // generate_seed(rng, thread), :817
+    int rc = bxg_population_generate_seeds(pop, workers, seeds.data());
+    for (int l = 0; rc == BXG_OK && l != workers; ++l)
+        rc = bxg_population_worker_seed(pop, l, seeds[l]);
+
+    const auto start = std::chrono::steady_clock::now();
+    struct report
+    {
+        const context* ctx;
+    } rep{ &ctx };
+    auto update = [](int remaining, double value, int64_t loop, double duration, int64_t restarts,
+                     void* user) {
+        const context& c = *static_cast<report*>(user)->ctx;
+        if (c.update)
+            c.update(remaining, value, static_cast<long int>(loop), duration, static_cast<long int>(restarts));
+    };
+    if (rc == BXG_OK)
+        rc = bxg_optimize(B, pop, nullptr, max_rounds > 0 ? 0.0 : ctx.parameters.time_limit, max_rounds,
+                          0, update, &rep, nullptr);
+    if (rc != BXG_OK) {
+        release();
+        throw solver_failure(solver_error_tag::no_solver_available);
+    }
+
+    r.strings = pb.strings;
+    r.affected_vars = pb.affected_vars;
+    r.variable_name = pb.vars.names;
+    r.variables = variables;
+    r.constraints = length(csts);
+
+    // :881-902
+    const int size = bxg_population_size(pop);
+    auto fill = [&](int i, solution& s, int* rem, long int* loop) {
+        try {
+            member_to_solution(pop, i, variables, s, rem, loop);
+        } catch (...) {
+            release();
+            throw;
+        }
+    };
+    int first_remaining = 0;
+    long int first_loop = 0;
+    switch (ctx.parameters.storage) {
+    case solver_parameters::storage_type::one:
+        r.solutions.resize(1);
+        fill(0, r.solutions[0], &first_remaining, &first_loop);
+        break;
+    case solver_parameters::storage_type::bound: {
+        r.solutions.resize(2);
+        fill(0, r.solutions[0], &first_remaining, &first_loop);
+        // get_worst, :328-337: the first member after the front that is not a solution
+        int last = 1, rem = 0;
+        solution probe;
+        while (last != size) {
+            fill(last, probe, &rem, nullptr);
+            if (rem != 0)
+                break;
+            ++last;
+        }
+        fill(last == size ? last - 1 : last, r.solutions[1], nullptr, nullptr);
+    } break;
+    case solver_parameters::storage_type::five:
+        r.solutions.resize(5);
+        fill(0, r.solutions[0], &first_remaining, &first_loop);
+        for (int i = 1; i != 5 && i < size; ++i)
+            fill(i, r.solutions[i], nullptr, nullptr);
+        break;
+    }
+    r.status = first_remaining == 0 ? result_status::success : result_status::time_limit_reached;
+    r.loop = first_loop;
+    r.remaining_constraints = first_remaining;
+    r.duration = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    release();
+
+    if (ctx.finish)
+        ctx.finish(r);
     return r;
 }
 

@@ -355,6 +355,9 @@ def ref_b200():
         lib = C.CDLL(os.path.join(HERE, "_ref", "libbxref_b200.so"))
         lib.bxref_solve_b200.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, _i8p, C.POINTER(C.c_double),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        lib.bxref_optimize_b200.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int,
+                                            _i8p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int * 3)]
         _ref["b200"] = lib
     return _ref["b200"]
 
@@ -519,6 +522,18 @@ class RefProblem:
                                          C.byref(loop))
         return {"status": st, "x": x, "value": value.value, "remaining": rem.value, "loop": loop.value}
 
+    def optimize_b200(self, seed: int, workers: int = 1, device: int = 0, time_limit: float = -1.0,
+                      max_rounds: int = 0, storage: int = 0):
+        """baryonyx::itm::optimize_b200 (integration/itm_b200.cpp): the reference's
+        optimize over the engine, its context callbacks counted."""
+        x = np.zeros(self.n, np.int8)
+        value, rem, nsol = C.c_double(), C.c_int(), C.c_int()
+        calls = (C.c_int * 3)()
+        st = ref_b200().bxref_optimize_b200(self.h, seed, workers, device, time_limit, max_rounds, storage, x,
+                                            C.byref(value), C.byref(rem), C.byref(nsol), C.byref(calls))
+        return {"status": st, "x": x, "value": value.value, "remaining": rem.value, "solutions": nsol.value,
+                "calls": {"start": calls[0], "update": calls[1], "finish": calls[2]}}
+
     def solve(self, seed: int):
         x = np.zeros(self.n, np.int8)
         value, rem = C.c_double(), C.c_int()
@@ -539,8 +554,12 @@ class RefProblem:
         upd, swp, sec = C.c_int64(), C.c_int64(), C.c_double()
         st = self.lib.bxref_optimize(self.h, seed, threads, time_limit, x, C.byref(value), C.byref(rem),
                                      C.byref(upd), C.byref(swp), C.byref(sec))
+        ff, rs = C.c_double(), C.c_int64()
+        self.lib.bxref_optimize_report.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        self.lib.bxref_optimize_report(C.byref(ff), C.byref(rs))
         return {"status": st, "x": x, "value": value.value, "remaining": rem.value,
-                "updates": upd.value, "sweeps": swp.value, "seconds": sec.value}
+                "updates": upd.value, "sweeps": swp.value, "seconds": sec.value,
+                "first_feasible_s": None if ff.value < 0 else ff.value, "restarts": rs.value}
 
     def optimize_trace(self, seed: int, rounds: int, population_size: int):
         """The reference's optimize_functor at thread = 1, stopped after `rounds`

@@ -118,6 +118,11 @@ int bxref_optimize(void* h, uint32_t seed, int threads, double time_limit,
                    int8_t* x, double* value, int* remaining, int64_t* updates,
                    int64_t* sweeps, double* seconds);
 
+/* Of the last bxref_optimize: seconds until the best member first had no violated
+ * row (-1: never; 1 s granularity, the reference's own ctx.update report) and
+ * the restarts its workers began. */
+void bxref_optimize_report(double* first_feasible_seconds, int64_t* restarts);
+
 /* Trace of the optimizer at thread = 1: the reference's own optimize_functor
  * (itm-optimizer-common.hpp:596-752) on the calling thread, set up as
  * optimize_problem does (:795-826), stopped after `rounds` restarts.  Snapshot

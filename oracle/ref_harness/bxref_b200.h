@@ -11,6 +11,13 @@ extern "C" {
  * of a bxref_open handle.  Returns result_status, or -100 - solver_error_tag. */
 int bxref_solve_b200(void* h, uint32_t seed, int restarts, int device, int8_t* x,
                      double* value, int* remaining, int64_t* loop);
+/* baryonyx::itm::optimize_b200(ctx{seed, time_limit, storage}, problem, workers,
+ * device, max_rounds): the reference's optimize over the engine.  calls[3] =
+ * how often ctx.start / ctx.update / ctx.finish were invoked.  Returns
+ * result_status, or -100 - solver_error_tag. */
+int bxref_optimize_b200(void* h, uint32_t seed, int workers, int device, double time_limit,
+                        int64_t max_rounds, int storage, int8_t* x, double* value,
+                        int* remaining, int* n_solutions, int* calls);
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,10 @@ struct trace_data
 };
 
 
+// last bxref_optimize: seconds until the population's best first had no violated
+// row (1 s granularity: the reference's own report), restarts begun; harness_eq01.cpp
+void optimize_report(double* first_feasible_seconds, int64_t* restarts);
+
 // Per-solver factories, defined in harness_<solver>.cpp.
 #define BXREF_DECLARE(tag)                                                   \
     run_base* make_run_##tag(handle& h, uint32_t seed);                       \

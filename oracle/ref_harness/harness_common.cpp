@@ -567,6 +567,13 @@ bxref_optimize(void* hv,
     return out.status;
 }
 
+void
+bxref_optimize_report(double* first_feasible_seconds, int64_t* restarts)
+{
+    // set by the per-solver translation units; read through any of them
+    bxref::optimize_report(first_feasible_seconds, restarts);
+}
+
 void*
 bxref_opt_trace(void* hv, uint32_t seed, int rounds)
 {

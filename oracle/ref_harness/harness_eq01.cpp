@@ -7,4 +7,13 @@
 
 namespace bxref {
 BXREF_DEFINE(eq01, solver_equalities_01coeff)
+
+void
+optimize_report(double* first_feasible_seconds, int64_t* restarts)
+{
+    if (first_feasible_seconds)
+        *first_feasible_seconds = g_first_feasible;
+    if (restarts)
+        *restarts = g_restarts;
+}
 }

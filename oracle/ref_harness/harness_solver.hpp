@@ -25,6 +25,8 @@ inline thread_local int64_t tl_updates = 0;
 inline thread_local int64_t tl_sweeps = 0;
 inline std::atomic<int64_t> g_updates{ 0 };
 inline std::atomic<int64_t> g_sweeps{ 0 };
+inline double g_first_feasible = -1.0; // of the last optimize_impl
+inline long int g_restarts = 0;
 
 // Shadows the two hot-path entry points to count constraint updates
 // (SURVEY.md 8c-2).  All arithmetic stays in Base.
@@ -286,9 +288,21 @@ optimize_impl(handle& h,
     g_sweeps = 0;
 
     auto start = std::chrono::steady_clock::now();
+    // the reference's own once-a-second report (itm-optimizer-common.hpp:835-853):
+    // when the best member first had no violated row, and how many restarts ran
+    double first_feasible = -1.0;
+    long int restarts = 0;
+    ctx.update = [&](int remaining, double, long int, double, long int calls) {
+        if (remaining == 0 && first_feasible < 0)
+            first_feasible =
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+        restarts = calls;
+    };
     result r =
       optimize_problem<counting<Solver>, double, Mode, Cost>(ctx, h.pb);
     auto end = std::chrono::steady_clock::now();
+    g_first_feasible = first_feasible;
+    g_restarts = restarts;
 
     fill_out(r, h.n, out);
     out.updates = g_updates.load();

@@ -94,3 +94,36 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "bx_oracle" not in text and "liboracle" not in text, f
                 assert "libbxref" not in text, f
+
+
+def test_lp_entry_points_never_throw_or_hang(tmp_path):
+    """Malformed input comes back as a status: a directory instead of a
+    file, truncated sections (the reference's own loops would spin on them), a
+    constant term that registers an empty name."""
+    with pytest.raises(capi.BxgError):
+        capi.read_lp(path=str(tmp_path))  # a directory
+    for text in ("minimize x + y st x + 3 <= 5 binary x",
+                 "minimize x + y st x + y <= 5 general x",
+                 "minimize x + y st x + y <= 5 bounds x <= 4",
+                 "minimize x + y",
+                 "minimize"):
+        with pytest.raises(capi.BxgError):
+            capi.read_lp(text=text)
+
+
+def test_problem_create_validates_the_csr_before_using_it():
+    """Decreasing / non-zero-based row_ptr, column out of range, zero factor:
+    BXG_E_INVALID before anything is sized from the arrays (no CUDA needed to get
+    that far or not, the answer is an error either way)."""
+    lib = capi.lib()
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    ok = dict(row_ptr=[0, 2, 4], col=[0, 1, 1, 2], factor=[1, 1, 1, 1], cmin=[1, 1], cmax=[1, 1])
+    bad = [dict(ok, row_ptr=[1, 2, 4]), dict(ok, row_ptr=[0, 3, 2]), dict(ok, row_ptr=[0, 0, 4]),
+           dict(ok, col=[0, 1, 1, 7]), dict(ok, factor=[1, 0, 1, 1])]
+    for case in bad:
+        h = C.c_void_p()
+        rc = lib.bxg_problem_create(2, 3, i32(case["row_ptr"]), i32(case["col"]), i32(case["factor"]),
+                                    i32(case["cmin"]), i32(case["cmax"]), 0, 0, 0, i32([0]),
+                                    np.zeros(1, np.float64), 0.0, 0, C.byref(h))
+        assert rc in (-1, -2), (case, rc)  # INVALID (or no CUDA device here)
+        assert not h.value
