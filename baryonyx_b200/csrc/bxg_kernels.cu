@@ -1257,6 +1257,9 @@ update_row_z(int k, double kappa, int push, double obj_amp)
                         need_cta = 1;
                     } else
                         selected = z_bb_solve(w, R, r_size, maximize, bkmin, bkmax);
+                } else if (pb.ex_count[k] >= 64) {
+                    z_ex_prepare(w, R, r_size);
+                    need_cta = 2;
                 } else
                     selected = z_ex_solve(w, R, r_size, maximize, pb.ex_flat + pb.ex_start[k],
                                           pb.ex_count[k]);
@@ -1266,7 +1269,17 @@ update_row_z(int k, double kappa, int push, double obj_amp)
         sh->tmp_i = need_cta;
     }
     __syncthreads();
-    if (sh->tmp_i) {
+    if (sh->tmp_i == 2) {
+        // (uniform) the feasible patterns of an exhaustive row, a share per thread
+        const ZWork w(L.zs, pb.max_zrow);
+        const int* masks = pb.ex_flat + pb.ex_start[k];
+        const int best = z_ex_enumerate(w, r_size, maximize, masks, pb.ex_count[k], sh->red, sh->redi);
+        if (tid == 0) {
+            const ZRow R{ L.sk, L.sid, pb.row_a + r0 };
+            sh->selected = best >= 0 ? z_ex_finish(w, R, r_size, maximize, masks[best])
+                                     : z_ex_solve(w, R, r_size, maximize, masks, pb.ex_count[k]);
+        }
+    } else if (sh->tmp_i) {
         // (uniform) every thread enumerates its share of the subsets
         const ZWork w(L.zs, pb.max_zrow);
         const int b0 = sh->redi[0], b1 = sh->redi[1];
@@ -1567,15 +1580,16 @@ order_run(Lane& L, Lists& ls, double kappa, int push, double obj_amp)
     // (the skipped scan is not counted as algorithmic bytes).
     if (len == 0 && order != ORDER_PI_SIGN_CHANGE)
         return 0;
+    // one way to read row i of the list, whichever form it has: plain rows,
+    // (row, amount) pairs, or pairs packed amount << 16 | row
+    const int* list = pairs ? (L.mop ? reinterpret_cast<const int*>(L.mop) : reinterpret_cast<const int*>(L.mo))
+                            : L.oR;
+    const int stride = pairs && !L.mop ? 2 : 1;
+    const int mask = pairs && L.mop ? 0xffff : 0x7fffffff;
+    const bool reversed = order == ORDER_REVERSING;
     for (int i = 0; i < len; ++i) {
-        int k;
-        if (pairs)
-            k = L.mop ? (int)(L.mop[i] & 0xffffu) : L.mo[i].x;
-        else
-            k = L.oR[order == ORDER_REVERSING ? len - 1 - i : i];
-        const int k_next = i + 1 < len ? (pairs ? (L.mop ? (int)(L.mop[i + 1] & 0xffffu) : L.mo[i + 1].x)
-                                                : L.oR[order == ORDER_REVERSING ? len - 2 - i : i + 1])
-                                       : -1;
+        const int k = list[(reversed ? len - 1 - i : i) * stride] & mask;
+        const int k_next = i + 1 < len ? (list[(reversed ? len - 2 - i : i + 1) * stride] & mask) : -1;
 #if BXG_FAM == 2
         (void)k_next;
         if (L.all_smem)

@@ -483,7 +483,92 @@ z_bb_finish(const ZWork& w, const ZRow& R, int r_size, bool maximize, unsigned c
     return z_finish(w, R, r_size, maximize);
 }
 
+// exhaustive_solver::solve (exhaustive-solver.hpp:185-252) by the whole CTA:
+// the pattern with the best sum, the first of them when sums are equal (the
+// reference keeps the incumbent unless strictly beaten).  items[] set up by
+// z_ex_prepare.  Returns the pattern's index, or -1 when a sum is NaN (the
+// sequential statement decides then).
+__device__ inline void
+z_ex_prepare(const ZWork& w, const ZRow& R, int r_size)
+{
+    for (int i = 0; i != r_size; ++i) {
+        ZItem it;
+        it.r = R.value(i);
+        it.sum_z = 0.0;
+        it.variable = R.sid[i];
+        it.factor = it.original_factor = R.factor(i);
+        it.result = 0;
+        w.items[i] = it;
+    }
+}
+
+__device__ inline int
+z_ex_enumerate(const ZWork& w, int r_size, bool maximize, const int* masks, int solutions, double* red_z,
+               int* red_m)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    double bz = 0.0;
+    int bi = -1, nan = 0;
+    auto better = [&](double z, int i, double oz, int oi) {
+        if (oi < 0)
+            return true;
+        if (z != oz)
+            return maximize ? z > oz : z < oz;
+        return i < oi;
+    };
+    for (int i = tid; i < solutions; i += T) {
+        const int mk = masks[i];
+        double z = 0.0;
+        for (int j = 0; j != r_size; ++j)
+            if ((mk >> j) & 1)
+                z = __dadd_rn(z, w.items[j].r);
+        nan |= z != z;
+        if (better(z, i, bz, bi)) {
+            bz = z;
+            bi = i;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double oz = __shfl_xor_sync(0xffffffffu, bz, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        if (oi >= 0 && better(oz, oi, bz, bi)) {
+            bz = oz;
+            bi = oi;
+        }
+    }
+    if (ln == 0) {
+        red_z[wp] = bz;
+        red_m[wp] = nan ? -2 : bi;
+    }
+    __syncthreads();
+    bz = red_z[0];
+    bi = red_m[0];
+    bool any_nan = bi == -2;
+    for (int v = 1; v < nw; ++v) {
+        const double oz = red_z[v];
+        const int oi = red_m[v];
+        if (oi == -2)
+            any_nan = true;
+        else if (oi >= 0 && (bi < 0 || better(oz, oi, bz, bi))) {
+            bz = oz;
+            bi = oi;
+        }
+    }
+    return any_nan ? -1 : bi;
+}
+
+__device__ inline int
+z_ex_finish(const ZWork& w, const ZRow& R, int r_size, bool maximize, int mask)
+{
+    for (int i = 0; i != r_size; ++i)
+        w.items[i].result = (mask >> i) & 1;
+    return z_finish(w, R, r_size, maximize);
+}
+
 } // namespace bxg
+
 
 
 #endif
