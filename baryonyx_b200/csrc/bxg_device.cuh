@@ -392,6 +392,159 @@ seq_std_sort(const A& a, int n, Less less)
         seq_insertion_sort(a, 0, n, less);
 }
 
+// ---------------------------------------------------------------------------
+// The same std::sort by the whole CTA, same result element for element.
+//
+// What libstdc++'s introsort does to a range depends only on that range: the
+// pivot (median of three moved to the front), the Hoare partition, the depth
+// budget.  The two parts a partition leaves are disjoint, so they can be worked
+// on at the same time; only the partition of one range is inherently a
+// two-pointer walk.  One thread per warp takes ranges from a shared stack,
+// partitions, pushes the right part and carries on with the left one, as the
+// reference's loop does (stl_algo.h:1935-1952).  The final insertion sort
+// (:1872-1885) never moves an element out of the <= 16-element range the
+// partitioning left it in -- everything to the left is not greater -- and it is
+// stable, so it is a stable insertion sort of every such range, done by the
+// thread that produced the range.  A range that runs out of depth is
+// heap-sorted (:1942-1945) by the thread that holds it.  Critical path: about
+// 2 n partition steps instead of n log n.
+// ---------------------------------------------------------------------------
+struct SortQueue
+{
+    int lock;
+    int top;
+    int busy;
+    int cap;    // tasks the stack holds
+    int* tasks; // {first, last, depth} each
+};
+
+// the sequential statement on a sub-range with its depth budget (also the
+// overflow path of the stack)
+template<typename A, typename Less>
+__device__ inline void
+seq_sort_range(const A& a, int first0, int last0, int depth0, Less less)
+{
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 1;
+    stack_first[0] = first0;
+    stack_last[0] = last0;
+    stack_depth[0] = depth0;
+    while (sp) {
+        --sp;
+        int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+        for (;;) {
+            if (last - first <= 16) {
+                seq_insertion_sort(a, first, last, less);
+                break;
+            }
+            if (depth == 0) {
+                seq_heap_sort(a, first, last, less);
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            seq_move_median_to_first(a, first, first + 1, mid, last - 1, less);
+            const int cut = seq_unguarded_partition(a, first + 1, last, first, less);
+            stack_first[sp] = cut;
+            stack_last[sp] = last;
+            stack_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+}
+
+// All threads of the CTA call; q lives in shared memory, q->tasks anywhere the
+// CTA can read and write.  Ends with a CTA barrier.
+template<typename A, typename Less>
+__device__ inline void
+cta_std_sort(const A& a, int n, Less less, SortQueue* q)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1)
+            ++lg;
+        q->lock = 0;
+        q->busy = 0;
+        q->top = 0;
+        if (n > 1) {
+            q->tasks[0] = 0;
+            q->tasks[1] = n;
+            q->tasks[2] = 2 * lg;
+            q->top = 1;
+        }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0 && n > 1) {
+        volatile int* vtop = &q->top;
+        volatile int* vbusy = &q->busy;
+        auto acquire = [&] {
+            while (atomicCAS(&q->lock, 0, 1) != 0)
+                ;
+            __threadfence_block();
+        };
+        auto release = [&] {
+            __threadfence_block();
+            atomicExch(&q->lock, 0);
+        };
+        for (;;) {
+            int first = -1, last = 0, depth = 0;
+            bool done = false;
+            acquire();
+            if (*vtop > 0) {
+                const int t = *vtop - 1;
+                *vtop = t;
+                first = q->tasks[3 * t];
+                last = q->tasks[3 * t + 1];
+                depth = q->tasks[3 * t + 2];
+                *vbusy = *vbusy + 1;
+            } else if (*vbusy == 0)
+                done = true;
+            release();
+            if (done)
+                break;
+            if (first < 0) {
+                __nanosleep(40);
+                continue;
+            }
+            for (;;) {
+                if (last - first <= 16) {
+                    seq_insertion_sort(a, first, last, less);
+                    break;
+                }
+                if (depth == 0) {
+                    seq_heap_sort(a, first, last, less);
+                    break;
+                }
+                --depth;
+                const int mid = first + (last - first) / 2;
+                seq_move_median_to_first(a, first, first + 1, mid, last - 1, less);
+                const int cut = seq_unguarded_partition(a, first + 1, last, first, less);
+                bool pushed = false;
+                acquire();
+                if (*vtop < q->cap) {
+                    const int t = *vtop;
+                    q->tasks[3 * t] = cut;
+                    q->tasks[3 * t + 1] = last;
+                    q->tasks[3 * t + 2] = depth;
+                    *vtop = t + 1;
+                    pushed = true;
+                }
+                release();
+                if (!pushed)
+                    seq_sort_range(a, cut, last, depth, less);
+                last = cut;
+            }
+            acquire();
+            *vbusy = *vbusy - 1;
+            release();
+        }
+    }
+    __syncthreads();
+}
+
 } // namespace bxg
+
 
 #endif

@@ -59,6 +59,7 @@ extern __shared__ __align__(16) unsigned char g_smem[];
 
 struct Shared
 {
+    SortQueue sq; // task stack of cta_std_sort
     uint32_t rng;
     int selected;
     int pi_changed;
@@ -109,6 +110,8 @@ struct Lane
     int* sid;                 // [sort_cap]  position in the row, moved with sk
     double* Rv;               // [max_row+2] value left at each slot of the reference's R
     double* pown;             // [max_row+1] theta-decayed P of the row's own entries
+    unsigned long long* xk;   // [max_row] workspace of the exact ordering in shared memory, or nullptr
+    int* xid;                 // [max_row]
     double* stage;            // [stage_cap] {P term, pi term} of the entries being summed
     int stage_cap;
     int* oR;
@@ -319,29 +322,28 @@ affect_scalars(Lane& L, int k, int selected, int r_size, double kappa, double v0
 // @region row_select_exact
 template<typename Less>
 __device__ __noinline__ void
-row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
+row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less,
+                 unsigned long long* wk, int* wid)
 {
+    // wk / wid: the row's keys and positions in row order (filled by the CTA),
+    // in shared memory when the plan found room for them: this is one thread
+    // doing some n log n dependent accesses
     const DevProblem& pb = *L.pb;
     const bool maximize = pb.maximize != 0;
     uint32_t rng = L.sh->rng;
-    Pairs a{ L.sk, L.sid };
-
-    for (int i = 0; i != r_size; ++i) {
-        L.sk[i] = L.key0[i];
-        L.sid[i] = i;
-    }
+    Pairs a{ wk, wid };
 
     auto value_at = [&](int p) {
-        return raw ? __longlong_as_double((long long)L.sk[p]) : value_of_key(L.sk[p], maximize);
+        return raw ? __longlong_as_double((long long)wk[p]) : value_of_key(wk[p], maximize);
     };
 
+    (void)less; // the CTA sorted wk / wid already (cta_std_sort: libstdc++'s std::sort, exactly)
     if (r_size > 1) {
-        seq_std_sort(a, r_size, less);
         // random_shuffle_unique, itm-common.hpp:117-132
         int ret = 0;
         int i = 1;
         for (; i != r_size; ++i) {
-            const bool differ = raw ? (value_at(ret) != value_at(i)) : (L.sk[ret] != L.sk[i]);
+            const bool differ = raw ? (value_at(ret) != value_at(i)) : (wk[ret] != wk[i]);
             if (differ) {
                 seq_shuffle(a, ret, i - ret, rng);
                 ret = i;
@@ -374,6 +376,26 @@ row_select_exact(Lane& L, int k, int r_size, double kappa, bool raw, Less less)
     const double vsel = selected >= 0 ? value_at(selected) : 0.0;
     const double vnext = (selected >= 0 && selected + 1 < r_size) ? value_at(selected + 1) : 0.0;
     affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
+}
+
+// calculator_sort's std::sort (itm-common.hpp:134-148) of the row's keys by the
+// whole CTA, with libstdc++'s exact result (cta_std_sort).  Out of line: its
+// stack must not weigh on the update's registers.
+__device__ __noinline__ void
+row_order_exact(Lane& L, unsigned long long* wk, int* wid, int r_size, bool raw, bool maximize)
+{
+    SortQueue* const q = &L.sh->sq;
+    if (threadIdx.x == 0) {
+        q->tasks = reinterpret_cast<int*>(L.stage);
+        q->cap = (int)(((size_t)L.stage_cap * sizeof(double2)) / (3 * sizeof(int)));
+    }
+    const Pairs a{ wk, wid };
+    if (!raw)
+        cta_std_sort(a, r_size, LessKey(), q);
+    else if (maximize)
+        cta_std_sort(a, r_size, LessRawMax(), q);
+    else
+        cta_std_sort(a, r_size, LessRawMin(), q);
 }
 
 // @region cta_bitonic_sort
@@ -532,10 +554,56 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
     }
     const bool any_reject = has_tie && __syncthreads_or(reject) != 0;
 
+    // A uniform draw was rejected somewhere (with runs of thousands of equal
+    // values the ranges reach n^2 and one draw in ten is): the draws are
+    // replayed one after the other.  The replay only needs the LENGTHS of the
+    // runs: the CTA lists the run starts (ordered compaction into the staging
+    // buffer, idle here), so the one thread walks a few runs instead of
+    // re-reading every key.
+    int* const runs = reinterpret_cast<int*>(L.stage);
+    const bool listed = any_reject && (size_t)(r_size + 2) * sizeof(int) <= (size_t)L.stage_cap * sizeof(double2);
+    int n_runs = 0;
+    if (listed) {
+        const int C = (r_size + T - 1) / T;
+        const int p0 = min(r_size, tid * C), p1 = min(r_size, p0 + C);
+        int mine = 0;
+        for (int p = p0; p < p1; ++p)
+            mine += p == 0 || L.sk[p] != L.sk[p - 1];
+        int incl = mine;
+        const int ln = tid & 31, wp = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln >= o)
+                incl += v;
+        }
+        __syncthreads(); // redi: the scan above is done with it
+        if (ln == 31)
+            L.sh->redi[wp] = incl;
+        __syncthreads();
+        int before = 0;
+        const int nw = T >> 5;
+        for (int w = 0; w < nw; ++w) {
+            const int v = L.sh->redi[w];
+            if (w < wp)
+                before += v;
+            n_runs += v;
+        }
+        int at = before + incl - mine;
+        for (int p = p0; p < p1; ++p)
+            if (p == 0 || L.sk[p] != L.sk[p - 1])
+                runs[at++] = p;
+        if (tid == 0)
+            runs[n_runs] = r_size;
+        __syncthreads();
+    }
+
     if (tid == 0) {
         uint32_t rng = rng0;
-        if (any_reject) {
-            // a uniform draw was rejected somewhere: replay the draws
+        if (listed) {
+            for (int j = 0; j != n_runs; ++j)
+                seq_shuffle_draws(runs[j + 1] - runs[j], rng);
+        } else if (any_reject) {
             int ret = 0;
             int i = 1;
             for (; i != r_size; ++i) {
@@ -1059,15 +1127,31 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         slow = L.sh->slow != 0;
     }
     if (slow) {
-        if (tid == 0) {
-            if (!raw)
-                row_select_exact(L, k, r_size, kappa, false, LessKey());
-            else if (maximize)
-                row_select_exact(L, k, r_size, kappa, true, LessRawMax());
-            else
-                row_select_exact(L, k, r_size, kappa, true, LessRawMin());
+        // the exact ordering by one thread: on a copy in shared memory when there is room
+        unsigned long long* const wk = L.xk ? L.xk : L.sk;
+        int* const wid = L.xk ? L.xid : L.sid;
+        for (int i = tid; i < r_size; i += T) {
+            wk[i] = L.key0[i];
+            wid[i] = i;
         }
         __syncthreads();
+        row_order_exact(L, wk, wid, r_size, raw, maximize);
+        if (tid == 0) {
+            if (!raw)
+                row_select_exact(L, k, r_size, kappa, false, LessKey(), wk, wid);
+            else if (maximize)
+                row_select_exact(L, k, r_size, kappa, true, LessRawMax(), wk, wid);
+            else
+                row_select_exact(L, k, r_size, kappa, true, LessRawMin(), wk, wid);
+        }
+        __syncthreads();
+        if (L.xk) {
+            for (int i = tid; i < r_size; i += T) {
+                L.sk[i] = wk[i];
+                L.sid[i] = wid[i];
+            }
+            __syncthreads();
+        }
     }
 
     // ---- D: x / P part of affect, by sorted position ------------------------
@@ -1665,7 +1749,7 @@ objective(Lane& L)
 // ---------------------------------------------------------------------------
 struct SmemPlan
 {
-    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem;
+    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem, exact_in_smem;
     int sort_cap;
     int stage_cap;
 };
@@ -1742,6 +1826,18 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
             s_x[i] = g_x[i];
     }
 
+    // workspace of the single-thread exact ordering (rows whose scratch is in
+    // global memory: every step of that thread would be an L2 round trip)
+    unsigned long long* s_xk = nullptr;
+    int* s_xid = nullptr;
+    if (plan.exact_in_smem) {
+        off = (off + 15) & ~size_t(15);
+        s_xk = reinterpret_cast<unsigned long long*>(smem + off);
+        off += sizeof(unsigned long long) * (size_t)pb.max_row;
+        s_xid = reinterpret_cast<int*>(smem + off);
+        off += sizeof(int) * (size_t)pb.max_row;
+    }
+
     // (Z) items / node stack / subvector pool of the sub-solvers: one thread
     // walks them node by node, so they belong in shared memory when they fit
     unsigned char* s_zs = nullptr;
@@ -1765,6 +1861,8 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.pb = &pb;
         L.pr = &pr;
         L.mop = s_mop;
+        L.xk = s_xk;
+        L.xid = s_xid;
         L.row_hdr = pb.row_hdr;
         L.row_info = pb.row_info;
         L.row_eptr = pb.row_eptr;
@@ -2430,7 +2528,7 @@ size_t z_scratch_bytes(int max_zrow);
 
 static size_t
 smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, int stage_cap, int mo_in = 0,
-           int z_in = 0)
+           int z_in = 0, int exact_in = 0)
 {
     size_t off = kLaneBytes + align16(sizeof(Shared));
     if (r_in) {
@@ -2443,6 +2541,8 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, in
     off += sizeof(int) * (size_t)pb.m;
     if (x_in)
         off += sizeof(uint32_t) * (size_t)pb.xw32;
+    if (exact_in)
+        off += 16 + 12 * (size_t)pb.max_row;
     if (z_in)
         off += 16 + z_scratch_bytes(pb.max_zrow);
     if (mo_in)
@@ -2493,6 +2593,7 @@ plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order)
     // memory when rows and amounts fit 16 bits each
     cfg.mo_in_smem = pairs_order && pb.m <= 0xffff && pb.max_amount <= 0xffff;
     cfg.z_in_smem = pb.max_zrow > 0 && z_scratch_bytes(pb.max_zrow) <= 8192;
+    cfg.exact_in_smem = 0;
     cfg.sort_cap = pow2_at_least(pb.max_row);
     // staging buffer of the reduced-cost gather: at least one column, at most
     // the longest row's entries
@@ -2501,7 +2602,7 @@ plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order)
     cfg.stage_cap = stage_min;
     auto bytes = [&]() {
         return smem_bytes(pb, cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.sort_cap,
-                          cfg.stage_cap, cfg.mo_in_smem, cfg.z_in_smem);
+                          cfg.stage_cap, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem);
     };
     // with the smallest staging buffer, drop the largest consumers first until
     // the plan fits
@@ -2516,8 +2617,13 @@ plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order)
     }
     if (bytes() > budget)
         cfg.pi_in_smem = 0;
-    if (!cfg.r_in_smem)
+    if (!cfg.r_in_smem) {
         cfg.stage_cap = stage_max; // the scratch lives in global memory
+        // ... except a copy of the keys for the single-thread exact ordering, when it fits
+        cfg.exact_in_smem = 1;
+        if (bytes() > budget)
+            cfg.exact_in_smem = 0;
+    }
     else {
         // then let the staging buffer grow (rows are summed in chunks when it
         // is shorter than the row's expansion): up to what lets seven lanes
@@ -2619,7 +2725,7 @@ BXG_FAM_FN(launch_begin)(const DevProblem& pb, const DevParams& pr, const DevBat
              int reset_solver, int init_on_device, double init_random,
              const double* d_cost_orig, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_begin, b.n_lanes, cfg, s, pb, pr, b, d_seeds, d_x0, d_rng, reset_solver,
                init_on_device, init_random, d_cost_orig, plan);
 }
@@ -2628,7 +2734,7 @@ void
 BXG_FAM_FN(launch_order_init)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                   int lane_first, int lane_count, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_order_init, lane_count, cfg, s, pb, pr, b, lane_first, plan);
 }
 
@@ -2636,7 +2742,7 @@ void
 BXG_FAM_FN(launch_sweep)(const DevProblem& pb, const DevParams& pr, const DevBatch& b, int push,
              double obj_amp, const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_sweep, b.n_lanes, cfg, s, pb, pr, b, push, obj_amp, plan);
 }
 
@@ -2644,7 +2750,7 @@ void
 BXG_FAM_FN(launch_solve)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
              const LaunchCfg& cfg, cudaStream_t s, int optimizer)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_solve, b.n_lanes, cfg, s, pb, pr, b, plan, optimizer);
 }
 
@@ -2652,7 +2758,7 @@ void
 BXG_FAM_FN(launch_optimize)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                 const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_HOT(k_optimize, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 
@@ -2660,7 +2766,7 @@ void
 BXG_FAM_FN(launch_objective)(const DevProblem& pb, const DevParams& pr, const DevBatch& b,
                  const LaunchCfg& cfg, cudaStream_t s)
 {
-    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.sort_cap, cfg.stage_cap };
+    SmemPlan plan{ cfg.pi_in_smem, cfg.x_in_smem, cfg.r_in_smem, cfg.mo_in_smem, cfg.z_in_smem, cfg.exact_in_smem, cfg.sort_cap, cfg.stage_cap };
     BXG_LAUNCH_COLD(k_objective, b.n_lanes, cfg, s, pb, pr, b, plan);
 }
 

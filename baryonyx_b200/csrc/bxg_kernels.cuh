@@ -211,7 +211,7 @@ struct LaunchCfg
 {
     int threads;
     size_t smem;
-    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem;
+    int pi_in_smem, x_in_smem, r_in_smem, mo_in_smem, z_in_smem, exact_in_smem;
     int sort_cap;
     int stage_cap;
 };
