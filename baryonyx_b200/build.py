@@ -20,7 +20,7 @@ UNITS = [("bxg_api.cu", "bxg_api.o", []),
          ("bxg_kernels.cu", "bxg_kernels_f2.o", ["-DBXG_FAM=2"])]
 SOURCES = ["bxg_api.cu", "bxg_kernels.cu"]
 OBJDIR = os.path.join(HERE, "build")
-HEADERS = ["bxg_device.cuh", "bxg_kernels.cuh", "bxg_zsolver.cuh", "bxg_population.cuh", "bxg_lp.hpp", os.path.join("..", "..", "include", "bxg.h")]
+HEADERS = ["bxg_device.cuh", "bxg_kernels.cuh", "bxg_zsolver.cuh", "bxg_population.cuh", "bxg_lp.hpp", "bxg_preprocess.hpp", os.path.join("..", "..", "include", "bxg.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

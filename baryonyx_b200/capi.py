@@ -81,6 +81,7 @@ EXPORTS = [
     "bxg_bit_array_hash",
     "bxg_lp_read", "bxg_lp_parse", "bxg_lp_destroy", "bxg_lp_info", "bxg_lp_rows", "bxg_lp_objective",
     "bxg_lp_variable", "bxg_lp_variables", "bxg_lp_names",
+    "bxg_lp_preprocess", "bxg_lp_affect", "bxg_lp_split", "bxg_lp_affected_count", "bxg_lp_affected",
 ]
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -530,10 +531,7 @@ class Population:
             self.h = C.c_void_p()
 
 
-def read_lp(path: str | None = None, text: str | None = None, pre_order: int = 0) -> dict:
-    """LP file (or text) -> the instance dict Problem takes: the engine's own
-    reader + constraint merging (bxg_lp_*), no device needed."""
-    L = lib()
+def _lp_types(L):
     L.bxg_lp_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.bxg_lp_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
     L.bxg_lp_destroy.argtypes = [C.c_void_p]
@@ -542,35 +540,96 @@ def read_lp(path: str | None = None, text: str | None = None, pre_order: int = 0
     L.bxg_lp_objective.argtypes = [C.c_void_p, _i32p, _f64p]
     L.bxg_lp_variable.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
     L.bxg_lp_variable.restype = C.c_char_p
+    L.bxg_lp_variables.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
+    L.bxg_lp_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bxg_lp_preprocess.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.bxg_lp_affect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.bxg_lp_split.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.bxg_lp_affected_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.bxg_lp_affected.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.bxg_lp_affected.restype = C.c_char_p
+
+
+def _lp_export(L, h) -> dict:
+    v = [C.c_int() for _ in range(5)]
+    cc, nobj = C.c_double(), C.c_int()
+    check(L.bxg_lp_info(h, *[C.byref(a) for a in v], C.byref(cc), C.byref(nobj)))
+    m, n, nnz, ptype, maximize = [a.value for a in v]
+    row_ptr = np.zeros(m + 1, np.int32)
+    col, fac = np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.int32)
+    cmin, cmax = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32)
+    check(L.bxg_lp_rows(h, row_ptr, col, fac, cmin, cmax))
+    ov, of = np.zeros(max(nobj.value, 1), np.int32), np.zeros(max(nobj.value, 1), np.float64)
+    check(L.bxg_lp_objective(h, ov, of))
+    lo, hi, ty = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+    check(L.bxg_lp_variables(h, lo, hi, ty))
+    need = C.c_size_t()
+    check(L.bxg_lp_names(h, None, 0, C.byref(need)))
+    raw = C.create_string_buffer(max(need.value, 1))
+    check(L.bxg_lp_names(h, raw, need.value, C.byref(need)))
+    names = raw.raw[: need.value].decode().split("\0")[:n]
+    bounds = list(zip(lo[:n].tolist(), hi[:n].tolist(), ty[:n].tolist()))
+    na = C.c_int()
+    check(L.bxg_lp_affected_count(h, C.byref(na)))
+    affected = []
+    for i in range(na.value):
+        val = C.c_int()
+        affected.append((L.bxg_lp_affected(h, i, C.byref(val)).decode(), val.value))
+    return {"m": m, "n": n, "row_ptr": row_ptr, "col": col[:nnz], "factor": fac[:nnz], "cmin": cmin[:m],
+            "cmax": cmax[:m], "problem_type": ptype, "maximize": maximize, "obj_var": ov[: nobj.value],
+            "obj_factor": of[: nobj.value], "cost_constant": cc.value, "names": names, "bounds": bounds,
+            "affected": affected}
+
+
+def read_lp(path: str | None = None, text: str | None = None, pre_order: int = 0, preprocess: bool = False,
+            affect: list | None = None) -> dict:
+    """LP file (or text) -> the instance dict Problem takes: the engine's own
+    reader + constraint merging (bxg_lp_*), no device needed.  preprocess: run
+    bxg_lp_preprocess on the parse (the reference's preprocessor "all");
+    affect: [(variable, value), ...] applied one after the other with
+    bxg_lp_affect on the result."""
+    L = lib()
+    _lp_types(L)
     h = C.c_void_p()
+    # BXG_LP_RAW (-1) in front of the preprocessor: the reference merges after it
+    first = -1 if preprocess else pre_order
     if path is not None:
-        check(L.bxg_lp_read(path.encode(), pre_order, C.byref(h)))
+        check(L.bxg_lp_read(path.encode(), first, C.byref(h)))
     else:
         raw = text.encode()
-        check(L.bxg_lp_parse(raw, len(raw), pre_order, C.byref(h)))
+        check(L.bxg_lp_parse(raw, len(raw), first, C.byref(h)))
     try:
-        v = [C.c_int() for _ in range(5)]
-        cc, nobj = C.c_double(), C.c_int()
-        check(L.bxg_lp_info(h, *[C.byref(a) for a in v], C.byref(cc), C.byref(nobj)))
-        m, n, nnz, ptype, maximize = [a.value for a in v]
-        row_ptr = np.zeros(m + 1, np.int32)
-        col, fac = np.zeros(max(nnz, 1), np.int32), np.zeros(max(nnz, 1), np.int32)
-        cmin, cmax = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32)
-        check(L.bxg_lp_rows(h, row_ptr, col, fac, cmin, cmax))
-        ov, of = np.zeros(max(nobj.value, 1), np.int32), np.zeros(max(nobj.value, 1), np.float64)
-        check(L.bxg_lp_objective(h, ov, of))
-        L.bxg_lp_variables.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
-        L.bxg_lp_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
-        lo, hi, ty = (np.zeros(max(n, 1), np.int32) for _ in range(3))
-        check(L.bxg_lp_variables(h, lo, hi, ty))
-        need = C.c_size_t()
-        check(L.bxg_lp_names(h, None, 0, C.byref(need)))
-        raw = C.create_string_buffer(max(need.value, 1))
-        check(L.bxg_lp_names(h, raw, need.value, C.byref(need)))
-        names = raw.raw[: need.value].decode().split("\0")[:n]
-        bounds = list(zip(lo[:n].tolist(), hi[:n].tolist(), ty[:n].tolist()))
-        return {"m": m, "n": n, "row_ptr": row_ptr, "col": col[:nnz], "factor": fac[:nnz], "cmin": cmin[:m],
-                "cmax": cmax[:m], "problem_type": ptype, "maximize": maximize, "obj_var": ov[: nobj.value],
-                "obj_factor": of[: nobj.value], "cost_constant": cc.value, "names": names, "bounds": bounds}
+        steps = ([("pp",)] if preprocess else []) + [("af", int(v), int(b)) for v, b in (affect or [])]
+        for i, st in enumerate(steps):
+            h2 = C.c_void_p()
+            order = pre_order if i + 1 == len(steps) else -1  # rows are merged once, at the end
+            if st[0] == "pp":
+                check(L.bxg_lp_preprocess(h, order, C.byref(h2)))
+            else:
+                check(L.bxg_lp_affect(h, st[1], st[2], order, C.byref(h2)))
+            L.bxg_lp_destroy(h)
+            h = h2
+        return _lp_export(L, h)
     finally:
         L.bxg_lp_destroy(h)
+
+
+def split_lp(path: str, variable: int, pre_order: int = 0, preprocess: bool = True) -> tuple:
+    """bxg_lp_split on the (preprocessed) parse: the two halves as instance dicts."""
+    L = lib()
+    _lp_types(L)
+    h = C.c_void_p()
+    check(L.bxg_lp_read(path.encode(), -1 if preprocess else pre_order, C.byref(h)))
+    hs = [h]
+    try:
+        if preprocess:
+            h2 = C.c_void_p()
+            check(L.bxg_lp_preprocess(h, -1, C.byref(h2)))
+            hs.append(h2)
+        a, b = C.c_void_p(), C.c_void_p()
+        check(L.bxg_lp_split(hs[-1], variable, pre_order, C.byref(a), C.byref(b)))
+        hs += [a, b]
+        return _lp_export(L, a), _lp_export(L, b)
+    finally:
+        for x in hs:
+            L.bxg_lp_destroy(x)

@@ -1618,4 +1618,5 @@ bxg_batch_launches(bxg_batch* b, int64_t* launches)
 } // extern "C"
 
 #include "bxg_lp.hpp"
+#include "bxg_preprocess.hpp"
 #include "bxg_population.cuh"

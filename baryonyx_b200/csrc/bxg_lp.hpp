@@ -450,6 +450,8 @@ struct bxg_lp
     std::vector<lp::variable> vars;
     std::vector<lp::row> rows; // as parsed, ids in file order
     int problem_type = 0;
+    // variables the preprocessor fixed (name, value): affected_variables, core:654-667
+    std::vector<std::pair<std::string, bool>> affected;
     // merged constraints (CSR)
     std::vector<int32_t> row_ptr{ 0 }, col, factor, cmin, cmax;
 };
@@ -696,7 +698,7 @@ lp_parse(std::string text, bxg_lp& out)
 std::string
 lp_merge(bxg_lp& p, int pre_order)
 {
-    if (pre_order < 0 || pre_order > 11)
+    if (pre_order < -1 || pre_order > 11)
         return "unknown pre_constraint_order";
     int coef = 0;
     bool inequality = false;
@@ -710,6 +712,11 @@ lp_merge(bxg_lp& p, int pre_order)
         }
     }
     p.problem_type = (inequality ? 3 : 0) + coef;
+    if (pre_order == -1) { // BXG_LP_RAW: the parse as it is, for bxg_lp_preprocess (the reference merges after its preprocessor)
+        p.row_ptr.assign(1, 0);
+        p.col.clear(), p.factor.clear(), p.cmin.clear(), p.cmax.clear();
+        return "";
+    }
 
     struct merged
     {

@@ -374,11 +374,15 @@ uint64_t bxg_bit_array_hash(int n, const uint64_t* x_words);
  * one [min, max] row.  pre_order = the reference's pre_constraint_order
  * (core:296-330): 0 none (rows in file order), 1 memory (+ elements of a row
  * sorted by variable), 2-7 rows grouped by type in the named order, 8-11
- * p1-p4 (rows and elements by cost / degree ratio).  Quadratic objectives are
+ * p1-p4 (rows and elements by cost / degree ratio); BXG_LP_RAW (-1): the parse
+ * alone, no rows merged or reported, as the input of bxg_lp_preprocess (the
+ * reference merges AFTER its preprocessor: rows the preprocessor removes
+ * cannot make the merge fail).  Quadratic objectives are
  * BXG_E_INVALID.  Host code, no device needed.
  * On a malformed file bxg_last_error() carries the reference's
  * file_format_error_tag name. */
 typedef struct bxg_lp bxg_lp;
+#define BXG_LP_RAW (-1)
 int bxg_lp_read(const char* path, int pre_order, bxg_lp** out);
 int bxg_lp_parse(const char* text, size_t length, int pre_order, bxg_lp** out);
 void bxg_lp_destroy(bxg_lp* lp);
@@ -396,6 +400,30 @@ const char* bxg_lp_variable(const bxg_lp* lp, int i, int* min, int* max, int* ty
  * buffer only asks for it) */
 int bxg_lp_variables(const bxg_lp* lp, int32_t* min, int32_t* max, int32_t* type);
 int bxg_lp_names(const bxg_lp* lp, char* buffer, size_t capacity, size_t* needed);
+
+/* ---- preprocessor ----
+ * What the reference runs in front of the solver when
+ * solver_parameters::preprocessor is "all" (lib/src/lpcore.cpp:89-130):
+ * bxg_lp_preprocess = baryonyx::preprocess (lib/src/preprocessor.cpp:893-903),
+ * bxg_lp_affect = baryonyx::affect (:876-891), bxg_lp_split = baryonyx::split
+ * (:857-874; the branch optimizer's step, lib/src/branch-optimizer.cpp:162-163).
+ * Variables fixed by their bounds, by rows with one free element or rows that
+ * force all their elements, and variables no live row uses; the result is a
+ * new handle over the remaining variables (renumbered in order), the rows that
+ * still have two or more free elements (right-hand sides reduced), the
+ * objective constant raised by the costs of the variables set to one, merged
+ * with pre_order like bxg_lp_read.  The fixed variables of a handle, those of
+ * the handle it was derived from first: bxg_lp_affected_count / bxg_lp_affected
+ * (result::affected_vars, core:727).  Same shrunk problem as the reference on
+ * its LP fixtures (tests/test_preprocess.py).  A row that cannot hold is
+ * BXG_E_INVALID (the reference's bx_reach()).  Host code, no device needed;
+ * the "preprocessed.lp" file the reference leaves in the working directory
+ * is not written. */
+int bxg_lp_preprocess(const bxg_lp* lp, int pre_order, bxg_lp** out);
+int bxg_lp_affect(const bxg_lp* lp, int variable, int value, int pre_order, bxg_lp** out);
+int bxg_lp_split(const bxg_lp* lp, int variable, int pre_order, bxg_lp** out_true, bxg_lp** out_false);
+int bxg_lp_affected_count(const bxg_lp* lp, int* count);
+const char* bxg_lp_affected(const bxg_lp* lp, int i, int* value);
 
 #ifdef __cplusplus
 }

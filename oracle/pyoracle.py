@@ -454,7 +454,8 @@ def read_opt_trace(lib, prefix, t, m, n, nnz, size):
 class RefProblem:
     """LP file -> reference parser -> merged constraints."""
 
-    def __init__(self, lp_path: str | None, params: Params, fast=False, inst: dict | None = None):
+    def __init__(self, lp_path: str | None, params: Params, fast=False, inst: dict | None = None,
+                 preprocess: bool = False, affect=None):
         """From an LP file (the reference's parser), or from an instance dict
         (bxref_open_arrays: raw_problem filled directly, for instances whose LP
         text the reference's parser takes minutes to read)."""
@@ -466,6 +467,29 @@ class RefProblem:
                 i32(inst["cmin"]), i32(inst["cmax"]), int(inst["maximize"]), len(inst["obj_var"]),
                 i32(inst["obj_var"]), np.ascontiguousarray(inst["obj_factor"], np.float64),
                 float(inst["cost_constant"]), C.byref(params))
+        elif preprocess:
+            # baryonyx::preprocess, then baryonyx::affect for every (variable, value)
+            # (lib/src/preprocessor.cpp:876-903).  The reference leaves a
+            # "preprocessed.lp" in the working directory: run from a scratch one.
+            f = self.lib.bxref_open_pp
+            f.argtypes = [C.c_char_p, C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                          C.c_char_p, C.c_int]
+            f.restype = C.c_void_p
+            aff = list(affect or [])
+            va = (C.c_int * max(1, len(aff)))(*[int(a[0]) for a in aff])
+            vb = (C.c_int * max(1, len(aff)))(*[int(a[1]) for a in aff])
+            err = C.create_string_buffer(512)
+            import tempfile
+            cwd = os.getcwd()
+            with tempfile.TemporaryDirectory() as scratch:
+                os.chdir(scratch)
+                try:
+                    self.h = f(os.path.abspath(os.path.join(cwd, lp_path)).encode(), C.byref(params), len(aff),
+                               va, vb, err, 512)
+                finally:
+                    os.chdir(cwd)
+            if not self.h:
+                raise RuntimeError(f"reference preprocessor: {err.value.decode()}")
         else:
             self.h = self.lib.bxref_open(lp_path.encode(), C.byref(params))
         if not self.h:
@@ -509,6 +533,18 @@ class RefProblem:
             names.append(f(self.h, i, C.byref(lo), C.byref(hi), C.byref(ty)).decode())
             bounds.append((lo.value, hi.value, ty.value))
         return names, bounds
+
+    def affected(self):
+        """[(name, value)] of problem::affected_vars (the preprocessor's fixed variables)."""
+        f = self.lib.bxref_affected
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        f.restype = C.c_char_p
+        self.lib.bxref_affected_count.argtypes = [C.c_void_p]
+        out = []
+        for i in range(self.lib.bxref_affected_count(self.h)):
+            v = C.c_int()
+            out.append((f(self.h, i, C.byref(v)).decode(), v.value))
+        return out
 
     def run(self, seed: int) -> "RefRun":
         return RefRun(self, seed)
@@ -720,3 +756,36 @@ class Population:
         if self.h:
             self._f("destroy")(self.h)
             self.h = None
+
+
+def ref_preprocess(lp_path: str, params: "Params", affect=None):
+    """The compiled reference's preprocess (+ affect chain) on an LP file, run in
+    a forked child: a contract failure inside the reference (bx_reach, bx_assert)
+    is std::terminate (lib/src/debug.hpp:52-62) and must not take the test
+    process with it.  -> ("ok", parse dict) | ("refuses", message) | ("aborts", None)"""
+    import pickle
+
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:
+        os.close(r)
+        try:
+            import faulthandler
+
+            faulthandler.disable()  # the abort of the child is an outcome, not a crash to report
+            os.dup2(os.open(os.devnull, os.O_WRONLY), 2)
+            h = RefProblem(lp_path, params, preprocess=True, affect=affect)
+            want = h.instance()
+            want["names"], want["bounds"] = h.variables()
+            want["affected"] = h.affected()
+            out = ("ok", want)
+        except RuntimeError as e:
+            out = ("refuses", str(e))
+        with os.fdopen(w, "wb") as f:
+            pickle.dump(out, f)
+        os._exit(0)
+    os.close(w)
+    with os.fdopen(r, "rb") as f:
+        data = f.read()
+    os.waitpid(pid, 0)
+    return pickle.loads(data) if data else ("aborts", None)

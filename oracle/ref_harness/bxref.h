@@ -66,6 +66,12 @@ void bxref_default_params(bxref_params* p);
 /* Problem handle: parse LP (reference parser), unpreprocess, clamp parameters
  * (context_set_solver_parameters), make_merged_constraints. */
 void* bxref_open(const char* lp_path, const bxref_params* p);
+/* the same behind baryonyx::preprocess and a chain of baryonyx::affect calls
+ * (lib/src/preprocessor.cpp:876-903); null + err on a contract failure */
+void* bxref_open_pp(const char* lp_path, const bxref_params* p, int n_affect,
+                    const int* variable, const int* value, char* err, int err_len);
+int bxref_affected_count(void* h);
+const char* bxref_affected(void* h, int i, int* value);
 /* The same from arrays (merged-constraint form), without the LP parser. */
 void* bxref_open_arrays(int m, int n, const int* row_ptr, const int* col,
                         const int* factor, const int* cmin, const int* cmax,

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <fstream>
 #include <limits>
 #include <string>
@@ -232,6 +233,86 @@ bxref_open(const char* lp_path, const bxref_params* p)
         h->nnz += length(c.elements);
 
     return h.release();
+}
+
+// The handle behind the reference's preprocessor: baryonyx::preprocess
+// (lib/src/preprocessor.cpp:893-903) on the parse, then baryonyx::affect
+// (:876-891) for every (variable, value) given, one after the other, then
+// make_merged_constraints.  A contract failure of the reference (bx_reach,
+// bx_assert: std::logic_error in this build) comes back as a null handle with
+// the message in err.  The reference writes "preprocessed.lp" into the working
+// directory as a side effect: callers chdir to a scratch directory first.
+void*
+bxref_open_pp(const char* lp_path,
+              const bxref_params* p,
+              int n_affect,
+              const int* variable,
+              const int* value,
+              char* err,
+              int err_len)
+{
+    auto note = [&](const char* what) {
+        if (err && err_len > 0) {
+            std::strncpy(err, what, static_cast<size_t>(err_len) - 1);
+            err[err_len - 1] = 0;
+        }
+    };
+    note("");
+    try {
+        auto h = std::make_unique<bxref::handle>();
+        {
+            auto ptr = make_context(3);
+            h->orig = to_reference(*p);
+            context_set_solver_parameters(ptr, h->orig);
+            h->ctx.parameters = context_get_solver_parameters(ptr);
+        }
+        std::ifstream ifs(lp_path);
+        if (!ifs.is_open()) {
+            note("file_not_found");
+            return nullptr;
+        }
+        h->raw = make_problem(h->ctx, ifs);
+        if (!h->raw) {
+            note("parse");
+            return nullptr;
+        }
+        h->pb = preprocess(h->ctx, h->raw);
+        for (int i = 0; i != n_affect; ++i) {
+            if (variable[i] < 0 || variable[i] >= length(h->pb.vars.values)) {
+                note("variable index out of range");
+                return nullptr;
+            }
+            h->pb = affect(h->ctx, h->pb, variable[i], value[i] != 0);
+        }
+        h->csts = itm::make_merged_constraints(h->ctx, h->pb);
+        h->m = length(h->csts);
+        h->n = length(h->pb.vars.values);
+        h->nnz = 0;
+        for (const auto& c : h->csts)
+            h->nnz += length(c.elements);
+        return h.release();
+    } catch (const std::exception& e) {
+        note(e.what());
+        return nullptr;
+    }
+}
+
+int
+bxref_affected_count(void* hv)
+{
+    return length(static_cast<bxref::handle*>(hv)->pb.affected_vars.names);
+}
+
+const char*
+bxref_affected(void* hv, int i, int* value)
+{
+    auto* h = static_cast<bxref::handle*>(hv);
+    if (i < 0 || i >= length(h->pb.affected_vars.names))
+        return nullptr;
+    thread_local std::string name;
+    name.assign(h->pb.affected_vars.names[i].data(), h->pb.affected_vars.names[i].size());
+    *value = h->pb.affected_vars.values[i] ? 1 : 0;
+    return name.c_str();
 }
 
 // The same handle from arrays: baryonyx::raw_problem filled directly, for

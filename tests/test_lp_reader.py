@@ -140,9 +140,20 @@ def test_missing_file():
 
 
 def test_unknown_pre_order():
-    for bad in (-1, 12):
+    for bad in (-2, 12):
         with pytest.raises(capi.BxgError):
             capi.read_lp(text="minimize\n x\nst\n c: x <= 1\nend\n", pre_order=bad)
+
+
+def test_raw_parse_reports_no_rows():
+    """BXG_LP_RAW (-1): the parse alone, the input of bxg_lp_preprocess; rows
+    that contradict each other are not an error before the merge."""
+    text = "minimize\n x + y\nst\n a: x + y = 1\n b: x + y = 2\nbinary\n x y\nend\n"
+    d = capi.read_lp(text=text, pre_order=-1)
+    assert d["m"] == 0 and d["n"] == 2 and d["names"] == ["x", "y"] and d["problem_type"] == 0
+    with pytest.raises(capi.BxgError) as e:
+        capi.read_lp(text=text, pre_order=0)
+    assert "multiple_constraint" in str(e.value)
 
 
 @pytest.mark.parametrize("make", [
