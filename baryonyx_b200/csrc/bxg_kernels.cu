@@ -112,6 +112,9 @@ struct Lane
     double* pown;             // [max_row+1] theta-decayed P of the row's own entries
     unsigned long long* xk;   // [max_row] workspace of the exact ordering in shared memory, or nullptr
     int* xid;                 // [max_row]
+    int xcap;                 // elements xk / xid hold
+    int xchunk;               // the largest power of two <= xcap: chunk of cta_bitonic_chunked
+    int tie_streak;           // consecutive tie-table passes over long rows that found equal values
     double* stage;            // [stage_cap] {P term, pi term} of the entries being summed
     int stage_cap;
     int* oR;
@@ -434,6 +437,126 @@ cta_bitonic_sort(unsigned long long* sk, int* sid, int n2)
     __syncthreads();
 }
 
+// @region cta_bitonic_chunked
+// The same order for rows whose scratch is in global memory, with the
+// exchanges done in shared memory a chunk at a time.  The network is the
+// "flip" form of the bitonic sort, every exchange ascending: positions past
+// n stand for +infinity and never move, so any n is sorted without padding
+// and an exchange that reaches past n is skipped.  Blocks up to CH elements
+// (a power of two) are exchanged in the chunk buffer wk / wid: one visit per
+// chunk sorts it completely (block sizes 2 .. CH), and for each larger block
+// size only the strides >= CH go through global memory (csplib022-shaped rows
+// of 16.7 k elements with CH = 16 384: two visits and one global step instead
+// of 120 passes over an L2-resident scratch).  Keys come from src in row
+// order; ids are generated.
+__device__ __forceinline__ void
+bitonic_exchange(unsigned long long* k, int* id, int i, int l)
+{
+    const unsigned long long a = k[i], b = k[l];
+    if (a > b) {
+        k[i] = b;
+        k[l] = a;
+        const int t = id[i];
+        id[i] = id[l];
+        id[l] = t;
+    }
+}
+
+// pairs (o, kk - 1 - o) of every block of kk elements
+__device__ __forceinline__ void
+bitonic_flip(unsigned long long* k, int* id, int len, int kk)
+{
+    const int hb = kk >> 1;
+    const int pairs = ((len + kk - 1) / kk) * hb;
+    for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+        const int b = t >> (31 - __clz(hb)), o = t & (hb - 1);
+        const int i = b * kk + o, l = b * kk + (kk - 1 - o);
+        if (l < len)
+            bitonic_exchange(k, id, i, l);
+    }
+}
+
+// pairs (i, i + j) with bit j of i clear
+__device__ __forceinline__ void
+bitonic_stride(unsigned long long* k, int* id, int len, int j)
+{
+    const int pairs = ((len + 2 * j - 1) / (2 * j)) * j;
+    for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        if (l < len)
+            bitonic_exchange(k, id, i, l);
+    }
+}
+
+// barrier between two steps: exchanges that stay inside 64 elements are done
+// by the warp that owns them in both steps
+__device__ __forceinline__ void
+bitonic_sync(int reach, int next_reach)
+{
+    if (reach > 32 || next_reach > 32)
+        __syncthreads();
+    else
+        __syncwarp();
+}
+
+__device__ __noinline__ void
+cta_bitonic_chunked(const unsigned long long* src, unsigned long long* gk, int* gid, int n,
+                    unsigned long long* wk, int* wid, int CH)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int nch = (n + CH - 1) / CH;
+    for (int c = 0; c < nch; ++c) {
+        const int base = c * CH;
+        const int len = n - base < CH ? n - base : CH;
+        for (int i = tid; i < len; i += T) {
+            wk[i] = src[base + i];
+            wid[i] = base + i;
+        }
+        __syncthreads();
+        for (int kk = 2; kk < 2 * len; kk <<= 1) {
+            bitonic_flip(wk, wid, len, kk);
+            bitonic_sync(kk >> 1, kk > 2 ? kk >> 2 : kk);
+            for (int j = kk >> 2; j > 0; j >>= 1) {
+                bitonic_stride(wk, wid, len, j);
+                bitonic_sync(j, j > 1 ? j >> 1 : kk);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += T) {
+            gk[base + i] = wk[i];
+            gid[base + i] = wid[i];
+        }
+        __syncthreads();
+    }
+    for (int kk = 2 * CH; kk < 2 * n; kk <<= 1) {
+        bitonic_flip(gk, gid, n, kk);
+        __syncthreads();
+        for (int j = kk >> 2; j >= CH; j >>= 1) {
+            bitonic_stride(gk, gid, n, j);
+            __syncthreads();
+        }
+        for (int c = 0; c < nch; ++c) {
+            const int base = c * CH;
+            const int len = n - base < CH ? n - base : CH;
+            for (int i = tid; i < len; i += T) {
+                wk[i] = gk[base + i];
+                wid[i] = gid[base + i];
+            }
+            __syncthreads();
+            for (int j = CH >> 1; j > 0; j >>= 1) {
+                bitonic_stride(wk, wid, len, j);
+                bitonic_sync(j, j > 1 ? j >> 1 : 64);
+            }
+            for (int i = tid; i < len; i += T) {
+                gk[base + i] = wk[i];
+                gid[base + i] = wid[i];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // @region row_select_sorted
 // Parallel statement of calculator_sort + select_variables: the whole CTA
 // sorts the keys, the shuffle draws are accounted with the LCG jump-ahead
@@ -447,12 +570,26 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
     const int tid = threadIdx.x, T = blockDim.x;
     const bool maximize = pb.maximize != 0;
 
-    for (int i = tid; i < n2; i += T) {
-        L.sk[i] = i < r_size ? L.key0[i] : ~0ull;
-        L.sid[i] = i;
+#if BXG_TIMERS
+    const long long t_sort0 = tid == 0 ? clock64() : 0;
+#endif
+    if (L.xk && L.xchunk >= 64) {
+        // scratch in global memory, a chunk buffer in shared memory
+        cta_bitonic_chunked(L.key0, L.sk, L.sid, r_size, L.xk, L.xid, L.xchunk);
+    } else {
+        for (int i = tid; i < n2; i += T) {
+            L.sk[i] = i < r_size ? L.key0[i] : ~0ull;
+            L.sid[i] = i;
+        }
+        __syncthreads();
+        cta_bitonic_sort(L.sk, L.sid, n2);
     }
-    __syncthreads();
-    cta_bitonic_sort(L.sk, L.sid, n2);
+#if BXG_TIMERS
+    // (ordered rows: phase 2 = the CTA sort, phase 3 = runs, draws and the window)
+    const long long t_sort1 = tid == 0 ? clock64() : 0;
+    if (tid == 0)
+        L.cyc_phase[2] += (unsigned long long)(t_sort1 - t_sort0);
+#endif
 
     // equal keys next to each other = a run random_shuffle_unique shuffles
     int tie = 0;
@@ -652,6 +789,9 @@ row_select_sorted(Lane& L, int k, int r_size, int n2, int n_pre, double kappa)
               (selected >= 0 && selected + 1 < r_size) ? value_of_key(L.sk[selected + 1], maximize) : 0.0;
             affect_scalars(L, k, selected, r_size, kappa, v0, vsel, vnext);
         }
+#if BXG_TIMERS
+        L.cyc_phase[3] += (unsigned long long)(clock64() - t_sort1);
+#endif
     }
     __syncthreads();
 }
@@ -826,8 +966,61 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         pown[i] = own;
     };
 
+// @region update_row.direct
+    // Rows whose scratch is in global memory (thousands of elements): staging
+    // the terms there would write and re-read 16 bytes per entry on top of
+    // the gather itself.  One thread per element instead, walking its column
+    // in CSC order -- P is CSC-ordered, so the column's P values and (row,
+    // sign) words are two contiguous runs -- with the same two accumulators,
+    // left to right: the same sums bit for bit, 12 bytes per entry.
+    if (!SM) {
+        const int* __restrict__ csc_rs = L.csc_rs;
+        constexpr int V = 4; // independent (word, P) load pairs per trip
+        for (int i = tid; i < r_size; i += T) {
+            const int4 info = row_info[r0 + i]; // c0, c1, own CSC position, column
+            const double cj = cost[info.w];
+            const int t_last = info.y - 1;
+            double sum_pi = 0.0, sum_p = 0.0, own = 0.0;
+            for (int t0 = info.x; t0 < info.y; t0 += V) {
+                int rs[V];
+                double p[V];
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const int t = t0 + u < t_last ? t0 + u : t_last;
+                    rs[u] = csc_rs[t];
+                    p[u] = gP[t];
+                }
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (t0 + u < info.y) {
+                        double a_pi = s_pi[rs[u] >> 1];
+                        double pv = p[u];
+                        if ((rs[u] >> 1) == k)
+                            pv = __dmul_rn(pv, theta);
+                        if (FAM != FAM_01 && (rs[u] & 1)) {
+                            pv = -pv;
+                            a_pi = -a_pi;
+                        }
+                        sum_pi = __dadd_rn(sum_pi, a_pi);
+                        sum_p = __dadd_rn(sum_p, pv);
+                        if (t0 + u == info.z)
+                            own = pv;
+                    }
+                }
+            }
+            finish(i, cj, __dsub_rn(__dsub_rn(cj, sum_pi), sum_p), own);
+        }
+        if (tid < nh.y)
+            ni = row_info[nh.x + tid];
+        __syncthreads();
+#if BXG_TIMERS
+        if (tid == 0)
+            t_gather = clock64();
+#endif
+    }
+
 // @region update_row.chunk
-    for (int ia = 0; ia < r_size;) {
+    for (int ia = 0; SM && ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
         int ib = r_size;
         const int fa = ia == 0 ? 0 : row_eptr[r0 + ia];
@@ -937,6 +1130,9 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     const double old_pi = s_pi[k];
     const int tab_gen0 = L.tab_gen;
     const int tab_dirty0 = L.tab_dirty;
+    // (read before the barrier: thread 0 writes them later in this update)
+    const int tie_streak0 = L.tie_streak;
+    const unsigned ordered0 = L.n_path[0] + L.n_path[1];
     const bool raw = __syncthreads_or(odd) != 0;
 #if BXG_TIMERS
     if (tid == 0)
@@ -981,6 +1177,13 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
             }
         }
     }
+
+    // Long rows that keep showing equal values (integer costs, csplib022-shaped)
+    // go to the ordered path without asking the table first -- it handles rows
+    // without ties as well, so this only chooses the cheaper route; one row in
+    // sixteen still asks, and a pass that finds no equal values resets the streak.
+    if (mode >= 2 && !SM && tie_streak0 >= 4 && (ordered0 & 15u) != 0)
+        mode = 1;
 
     if (mode >= 2) {
 // @region update_row.ties
@@ -1046,6 +1249,8 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         const bool any_dup = __syncthreads_or(dup) != 0;
         if (tid == 0) {
             L.tab_gen = tab_gen;
+            if (!SM)
+                L.tie_streak = any_dup ? tie_streak0 + 1 : 0;
 #if BXG_TIMERS
             t_ties = clock64();
 #endif
@@ -1117,8 +1322,14 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         for (int i = tid; i < r_size; i += T)
             L.key0[i] = key_of(__longlong_as_double((long long)L.key0[i]), maximize);
     }
-    if (tid == 0)
+    if (tid == 0) {
         L.tab_dirty = 1;
+#if BXG_TIMERS
+        // ordered rows: phase 0 = gather, phase 1 = column sums (+ a tie table that found equal values)
+        L.cyc_phase[0] += (unsigned long long)(t_gather - t_start);
+        L.cyc_phase[1] += (unsigned long long)(clock64() - t_gather);
+#endif
+    }
     __syncthreads();
 
     bool slow = mode == 0;
@@ -1128,8 +1339,9 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     }
     if (slow) {
         // the exact ordering by one thread: on a copy in shared memory when there is room
-        unsigned long long* const wk = L.xk ? L.xk : L.sk;
-        int* const wid = L.xk ? L.xid : L.sid;
+        const bool in_smem = L.xk && r_size <= L.xcap;
+        unsigned long long* const wk = in_smem ? L.xk : L.sk;
+        int* const wid = in_smem ? L.xid : L.sid;
         for (int i = tid; i < r_size; i += T) {
             wk[i] = L.key0[i];
             wid[i] = i;
@@ -1145,7 +1357,7 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
                 row_select_exact(L, k, r_size, kappa, true, LessRawMin(), wk, wid);
         }
         __syncthreads();
-        if (L.xk) {
+        if (in_smem) {
             for (int i = tid; i < r_size; i += T) {
                 L.sk[i] = wk[i];
                 L.sid[i] = wid[i];
@@ -1833,9 +2045,9 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
     if (plan.exact_in_smem) {
         off = (off + 15) & ~size_t(15);
         s_xk = reinterpret_cast<unsigned long long*>(smem + off);
-        off += sizeof(unsigned long long) * (size_t)pb.max_row;
+        off += sizeof(unsigned long long) * (size_t)plan.exact_in_smem;
         s_xid = reinterpret_cast<int*>(smem + off);
-        off += sizeof(int) * (size_t)pb.max_row;
+        off += sizeof(int) * (size_t)plan.exact_in_smem;
     }
 
     // (Z) items / node stack / subvector pool of the sub-solvers: one thread
@@ -1863,6 +2075,12 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         L.mop = s_mop;
         L.xk = s_xk;
         L.xid = s_xid;
+        L.xcap = s_xk ? plan.exact_in_smem : 0;
+        L.xchunk = 0;
+        while (L.xcap >= 2 && (2 << L.xchunk) <= L.xcap)
+            ++L.xchunk;
+        L.xchunk = L.xcap >= 2 ? 1 << L.xchunk : 0;
+        L.tie_streak = 0;
         L.row_hdr = pb.row_hdr;
         L.row_info = pb.row_info;
         L.row_eptr = pb.row_eptr;
@@ -2541,8 +2759,8 @@ smem_bytes(const DevProblem& pb, int pi_in, int x_in, int r_in, int sort_cap, in
     off += sizeof(int) * (size_t)pb.m;
     if (x_in)
         off += sizeof(uint32_t) * (size_t)pb.xw32;
-    if (exact_in)
-        off += 16 + 12 * (size_t)pb.max_row;
+    if (exact_in) // (a capacity in elements)
+        off += 16 + 12 * (size_t)exact_in;
     if (z_in)
         off += 16 + z_scratch_bytes(pb.max_zrow);
     if (mo_in)
@@ -2620,9 +2838,11 @@ plan_launch(const DevProblem& pb, int device, int n_lanes, int pairs_order)
     if (!cfg.r_in_smem) {
         cfg.stage_cap = stage_max; // the scratch lives in global memory
         // ... except a copy of the keys for the single-thread exact ordering, when it fits
-        cfg.exact_in_smem = 1;
-        if (bytes() > budget)
-            cfg.exact_in_smem = 0;
+        // (a capacity in elements: the whole row when it fits, else what is left
+        // -- the chunk buffer of the CTA-wide sort, cta_bitonic_chunked)
+        const size_t fixed = bytes();
+        const size_t room = fixed + 64 < budget ? (budget - fixed - 64) / 12 : 0;
+        cfg.exact_in_smem = room >= (size_t)pb.max_row ? pb.max_row : (room >= 1024 ? (int)room : 0);
     }
     else {
         // then let the staging buffer grow (rows are summed in chunks when it

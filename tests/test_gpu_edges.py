@@ -67,3 +67,21 @@ def test_more_lanes_than_one_wave():
         assert out["status"][l] == o["status"] and out["loop"][l] == o["loop"], l
         assert np.array_equal(bt.best(l), o["x"]), l
     bt.close(), pb.close(), op.close()
+
+
+@pytest.mark.parametrize("m, n, lo, hi, sweeps", [
+    (8, 20000, 2, 4, 8),    # rows of ~7.5 k elements: two chunks of the shared-memory buffer
+    (6, 60000, 3, 5, 5),    # rows of ~40 k: three chunks, strides that cross chunks in global memory
+    (4, 64000, 3, 4, 4),    # rows of ~56 k: close to the longest the CTA-wide sort takes (16-bit positions)
+])
+def test_rows_whose_scratch_is_in_global_memory(m, n, lo, hi, sweeps):
+    """Rows too long for a shared-memory scratch (update_row's direct gather,
+    cta_bitonic_chunked, the tie-table shortcut): integer costs, so equal values
+    everywhere, +-1 factors; state equal to the oracle's after every sweep."""
+    inst = synth.csplib022(m=m, n=n, lo=lo, hi=hi, seed=31 + m, name="long-rows")
+    lockstep_engine(inst, util.params(kappa_step=0.01), [3, 4], sweeps, pushes_every=3)
+    # inequality rows of the same shape (selection window, stopping values)
+    inst = synth.csplib022(m=m, n=n, lo=lo, hi=hi, seed=41 + m, name="long-rows-ineq")
+    inst["cmin"] = (np.asarray(inst["cmin"]) - 1).astype(np.int32)
+    inst["problem_type"] = 4  # inequalities_101
+    lockstep_engine(inst, util.params(kappa_step=0.02), [5], sweeps)
