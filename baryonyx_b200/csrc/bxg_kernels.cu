@@ -67,6 +67,7 @@ struct Shared
     int list_len;
     int order_state;
     int tmp_i;
+    int n_dup; // equal keys listed by the tie table of the current row (update_row, mode 4)
     int slow; // the current row goes to the single-thread path
     int stop;    // the deadline has passed (time_limit / stop_task)
     int x_dirty; // a bit of x changed since x_value / x_hash were computed
@@ -870,6 +871,112 @@ merge_min2(unsigned long long& m1, unsigned long long& m2, unsigned long long o1
     m2 = hi < s2 ? hi : s2;
 }
 
+// @region cta_rank_select
+// The key of rank `rank` (0-based, ascending) among keys[0..n) by the whole
+// CTA, without ordering them: most-significant-digit-first radix select, eight
+// bits a pass, a 256-bin histogram in shared memory (equal digits of a warp
+// are counted with one atomic).  Returns the key; `mult` = how many elements
+// hold it, `pos` = the rank's offset inside that group of equal keys; `next`
+// = the smallest key above it (~0 when none).  What nth_element would give
+// the reference if calculator_sort were not a full sort: enough when the
+// equal-value runs of the row are known separately (update_row, mode 4).
+__device__ __noinline__ unsigned long long
+cta_rank_select(const unsigned long long* keys, int n, int rank, uint32_t* hist, Shared* sh, int& mult,
+                int& pos, unsigned long long& next)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ln = tid & 31, wp = tid >> 5, nw = T >> 5;
+    unsigned long long prefix = 0, decided = 0;
+    int r = rank, cnt = n;
+    for (int shift = 56; shift >= 0 && cnt > 1; shift -= 8) {
+        for (int i = tid; i < 256; i += T)
+            hist[i] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += T) {
+            const int i = i0 + tid;
+            unsigned d = 256u;
+            if (i < n) {
+                const unsigned long long key = keys[i];
+                if ((key & decided) == prefix)
+                    d = (unsigned)(key >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (d < 256u && ln == __ffs(peers) - 1)
+                atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        if (wp == 0) {
+            uint32_t c[8];
+            int s = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                c[u] = hist[ln * 8 + u];
+                s += (int)c[u];
+            }
+            int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (ln >= o)
+                    incl += v;
+            }
+            int acc = incl - s;
+            if (acc <= r && r < incl) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (r >= acc && r < acc + (int)c[u]) {
+                        sh->redi[0] = ln * 8 + u;
+                        sh->redi[1] = r - acc;
+                        sh->redi[2] = (int)c[u];
+                    }
+                    acc += (int)c[u];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)(unsigned)sh->redi[0] << shift;
+        decided |= 255ull << shift;
+        r = sh->redi[1];
+        cnt = sh->redi[2];
+        __syncthreads(); // redi and hist are rewritten by the next pass
+    }
+    // the (first) element under the prefix is the key; the smallest key above it
+    unsigned long long mine = ~0ull, above = ~0ull;
+    for (int i = tid; i < n; i += T) {
+        const unsigned long long key = keys[i];
+        if ((key & decided) == prefix)
+            mine = key < mine ? key : mine;
+    }
+    mine = warp_min_u64(mine);
+    if (ln == 0)
+        sh->redk[wp][0] = mine;
+    __syncthreads();
+    unsigned long long sel = sh->redk[0][0];
+    for (int w = 1; w < nw; ++w) {
+        const unsigned long long o = sh->redk[w][0];
+        sel = o < sel ? o : sel;
+    }
+    for (int i = tid; i < n; i += T) {
+        const unsigned long long key = keys[i];
+        if (key > sel)
+            above = key < above ? key : above;
+    }
+    above = warp_min_u64(above);
+    if (ln == 0)
+        sh->redk[wp][1] = above;
+    __syncthreads();
+    above = sh->redk[0][1];
+    for (int w = 1; w < nw; ++w) {
+        const unsigned long long o = sh->redk[w][1];
+        above = o < above ? o : above;
+    }
+    __syncthreads(); // redk is reused by the caller
+    mult = cnt;
+    pos = r;
+    next = above;
+    return sel;
+}
+
 // @region update_row.head
 // One constraint update (the loop body of compute_update_row /
 // push_and_compute_update_row).  Called by all threads of the CTA.
@@ -901,9 +1008,15 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     const int4* __restrict__ row_info = L.row_info;
     const int* __restrict__ row_eptr = L.row_eptr;
     // shared-memory views (the Lane block itself always lives there)
-    const int stage_cap = L.stage_cap;
-    // [stage_cap] {P term, pi term} of the column entries being summed
-    double2* const st = reinterpret_cast<double2*>(view<SM>(L.stage, L.o_stage));
+    // [stage_cap] {P term, pi term} of the column entries being summed.  Rows
+    // whose scratch is in global memory stage them in the shared-memory
+    // workspace of the exact ordering (xk / xid, one block, idle during the
+    // gather), a chunk of elements at a time.
+    const int x_entries = SM || !L.xk ? 0 : (int)(((size_t)L.xcap * 12u) / sizeof(double2));
+    const bool staged = SM || (x_entries >= 256 && x_entries >= L.pb->max_col);
+    const int stage_cap = SM ? L.stage_cap : x_entries;
+    double2* const st =
+      SM ? reinterpret_cast<double2*>(view<SM>(L.stage, L.o_stage)) : reinterpret_cast<double2*>(L.xk);
     double* const s_pi = view<SM>(L.pi, L.o_pi);
     unsigned long long* const key0 = view<SM>(L.key0, L.o_key0);
     double* const pown = view<SM>(L.pown, L.o_pown);
@@ -967,13 +1080,16 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     };
 
 // @region update_row.direct
-    // Rows whose scratch is in global memory (thousands of elements): staging
-    // the terms there would write and re-read 16 bytes per entry on top of
-    // the gather itself.  One thread per element instead, walking its column
-    // in CSC order -- P is CSC-ordered, so the column's P values and (row,
-    // sign) words are two contiguous runs -- with the same two accumulators,
-    // left to right: the same sums bit for bit, 12 bytes per entry.
-    if (!SM) {
+    // Rows whose scratch is in global memory and that have no shared-memory
+    // workspace to stage in: staging the terms in global memory would write
+    // and re-read 16 bytes per entry on top of the gather itself.  One thread
+    // per element instead, walking its column in CSC order -- P is
+    // CSC-ordered, so the column's P values and (row, sign) words are two
+    // contiguous runs -- with the same two accumulators, left to right: the
+    // same sums bit for bit, 12 bytes per entry.  (Every load instruction
+    // touches 32 different sectors: bound by the L1 wavefronts, 830 k cycles
+    // for a 16.7 k-element row -- the staged gather below is preferred.)
+    if (!staged) {
         const int* __restrict__ csc_rs = L.csc_rs;
         constexpr int V = 4; // independent (word, P) load pairs per trip
         for (int i = tid; i < r_size; i += T) {
@@ -1020,7 +1136,7 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     }
 
 // @region update_row.chunk
-    for (int ia = 0; SM && ia < r_size;) {
+    for (int ia = 0; staged && ia < r_size;) {
         // elements [ia, ib) whose entries fit the staging buffer
         int ib = r_size;
         const int fa = ia == 0 ? 0 : row_eptr[r0 + ia];
@@ -1184,6 +1300,25 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
     // sixteen still asks, and a pass that finds no equal values resets the streak.
     if (mode >= 2 && !SM && tie_streak0 >= 4 && (ordered0 & 15u) != 0)
         mode = 1;
+    // mode 4: the boundary lies inside the row, but `selected` is known before
+    // any ordering (an equality row, or an inequality row without zeros).  When
+    // all values differ -- or only a few are equal, kRankDups at most, and
+    // their run does not straddle the boundary -- affect needs the key of rank
+    // `selected`, the next key above it and the smallest one, and the engine
+    // needs the lengths of the few equal-value runs in ascending order: a
+    // radix select (cta_rank_select) and a list of the equal keys the tie
+    // table meets, instead of ordering thousands of elements.  Rows whose
+    // scratch is in global memory only (the short ones sort in a few
+    // thousand cycles); keys in the shared-memory workspace of the exact
+    // ordering, idle here.
+    constexpr int kRankDups = 48;
+    unsigned long long* dup_keys = nullptr;
+    if (!SM && mode == 1 && selected > 0 && L.xk && r_size <= L.xcap && L.xcap >= 1024 &&
+        !(tie_streak0 >= 4 && (ordered0 & 15u) != 0)) {
+        mode = 4;
+        // (xid: 256 histogram bins, then the list of equal keys)
+        dup_keys = reinterpret_cast<unsigned long long*>(L.xid + 256);
+    }
 
     if (mode >= 2) {
 // @region update_row.ties
@@ -1206,6 +1341,8 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         int dup = 0;
         for (int i = tid; i < r_size; i += T) {
             const unsigned long long bits = key0[i];
+            if (!SM && mode == 4)
+                L.xk[i] = key_of(__longlong_as_double((long long)bits), maximize);
             uint32_t h = ((uint32_t)bits ^ (uint32_t)(bits >> 32)) * 0x9E3779B1u;
             h = (h >> (32 - tab_bits)) & mask;
             const uint32_t mine = (gen << 16) | (uint32_t)(i + 1);
@@ -1222,6 +1359,12 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
                 const int other = (int)(cur & 0xffffu) - 1;
                 if (key0[other] == bits) {
                     dup = 1;
+                    if (!SM && mode == 4) {
+                        // one entry per element past the first of its run
+                        const int slot = atomicAdd(&sh->n_dup, 1);
+                        if (slot < kRankDups)
+                            dup_keys[slot] = key_of(__longlong_as_double((long long)bits), maximize);
+                    }
                     break;
                 }
                 h = (h + 1u) & mask;
@@ -1232,7 +1375,7 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         // candidates over the warp: mode 2 = the two smallest keys, mode 3 =
         // (largest non-stopping key, complemented; smallest stopping key)
         unsigned long long a, b;
-        if (mode == 2) {
+        if (mode != 3) {
             a = warp_min_u64(ca);
             // one holder of the minimum gives it up, everybody else keeps theirs
             const unsigned holders = __ballot_sync(0xffffffffu, ca == a);
@@ -1247,33 +1390,87 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
             sh->redk[wp][1] = b;
         }
         const bool any_dup = __syncthreads_or(dup) != 0;
-        if (tid == 0) {
-            L.tab_gen = tab_gen;
-            if (!SM)
-                L.tie_streak = any_dup ? tie_streak0 + 1 : 0;
-#if BXG_TIMERS
-            t_ties = clock64();
-#endif
-        }
+        bool ordered = any_dup; // equal values: their runs draw from the engine
         if (any_dup)
-            mode = 1; // equal values: their runs draw from the engine
+            mode = mode == 4 ? 4 : 1;
         else {
             a = sh->redk[0][0];
             b = sh->redk[0][1];
             for (int w = 1; w < nw; ++w) {
                 const unsigned long long oa = sh->redk[w][0], ob = sh->redk[w][1];
-                if (mode == 2)
+                if (mode != 3)
                     merge_min2(a, b, oa, ob);
                 else {
                     a = oa < a ? oa : a;
                     b = ob < b ? ob : b;
                 }
             }
+        }
+        unsigned long long key_sel = 0;
+        double v0 = 0.0, vsel = 0.0, vnext = 0.0;
+        if (!SM && mode == 4) {
+// @region update_row.rank
+            const int n_dup = any_dup ? sh->n_dup : 0;
+            if (any_dup) {
+                // (the candidates of the warps were not merged above)
+                a = sh->redk[0][0];
+                for (int w = 1; w < nw; ++w)
+                    a = sh->redk[w][0] < a ? sh->redk[w][0] : a;
+            }
+            __syncthreads(); // redk, n_dup read by everybody
+            if (n_dup > kRankDups)
+                mode = 1; // many equal values (integer costs, first sweeps): the ordered path
+            else {
+                int mult, pos;
+                unsigned long long above;
+                key_sel = cta_rank_select(L.xk, r_size, selected, reinterpret_cast<uint32_t*>(L.xid), sh,
+                                          mult, pos, above);
+                if (selected + 1 < r_size && pos + 1 < mult)
+                    mode = 0; // equal values on both sides of the boundary: the exact permutations decide
+                else {
+                    ordered = false;
+                    v0 = value_of_key(a, maximize);
+                    vsel = value_of_key(key_sel, maximize);
+                    vnext = selected + 1 < r_size ? value_of_key(above, maximize) : 0.0;
+                    if (tid == 0 && n_dup) {
+                        // random_shuffle_unique's draws: the runs of equal values in
+                        // ascending order, each one element longer than its entries here
+                        for (int i = 1; i < n_dup; ++i) {
+                            const unsigned long long key = dup_keys[i];
+                            int j = i;
+                            for (; j > 0 && dup_keys[j - 1] > key; --j)
+                                dup_keys[j] = dup_keys[j - 1];
+                            dup_keys[j] = key;
+                        }
+                        uint32_t rng = sh->rng;
+                        for (int i = 0; i < n_dup;) {
+                            int j = i + 1;
+                            while (j < n_dup && dup_keys[j] == dup_keys[i])
+                                ++j;
+                            seq_shuffle_draws(j - i + 1, rng);
+                            i = j;
+                        }
+                        sh->rng = rng;
+                    }
+                }
+            }
+            if (tid == 0)
+                sh->n_dup = 0;
+        }
+        if (tid == 0) {
+            L.tab_gen = tab_gen;
+            if (!SM)
+                L.tie_streak = ordered ? tie_streak0 + 1 : 0;
+#if BXG_TIMERS
+            t_ties = clock64();
+#endif
+        }
+        if (!ordered) {
 // @region update_row.scalars
             // every thread derives the same scalars; thread 0 publishes pi
-            unsigned long long key_sel;
-            double v0, vsel = 0.0, vnext = 0.0;
-            if (mode == 2) {
+            if (mode == 4) {
+                // (cta_rank_select gave them)
+            } else if (mode == 2) {
                 v0 = value_of_key(a, maximize);
                 vsel = v0;
                 vnext = value_of_key(b, maximize);
@@ -1302,10 +1499,11 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
             }
             __syncthreads();
             if (tid == 0) {
-                L.n_path[mode] += 1;
+                const int path = mode == 4 ? 2 : mode; // (counted with the other unordered rows)
+                L.n_path[path] += 1;
 #if BXG_TIMERS
                 const long long t_end = clock64();
-                L.cyc_path[mode] += (unsigned long long)(t_end - t_start);
+                L.cyc_path[path] += (unsigned long long)(t_end - t_start);
                 L.cyc_phase[0] += (unsigned long long)(t_gather - t_start);
                 L.cyc_phase[1] += (unsigned long long)(t_sums - t_gather);
                 L.cyc_phase[2] += (unsigned long long)(t_ties - t_sums);
@@ -2142,6 +2340,7 @@ lane_open(Lists& ls, const DevProblem& pb, const DevParams& pr, const DevBatch& 
         sh->pi_changed = 0;
         sh->remaining = ctl->remaining;
         sh->stop = 0;
+        sh->n_dup = 0;
         sh->x_dirty = 1;
         L.updates = 0;
         L.sweeps = 0;

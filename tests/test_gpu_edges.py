@@ -85,3 +85,23 @@ def test_rows_whose_scratch_is_in_global_memory(m, n, lo, hi, sweeps):
     inst["cmin"] = (np.asarray(inst["cmin"]) - 1).astype(np.int32)
     inst["problem_type"] = 4  # inequalities_101
     lockstep_engine(inst, util.params(kappa_step=0.02), [5], sweeps)
+
+
+@pytest.mark.parametrize("decimals", [None, 3, 1])
+def test_long_rows_rank_select(decimals):
+    """Long rows whose values differ, or with a few equal values only (real
+    costs, rounded to `decimals` places): the boundary inside the row is found
+    by the radix select (update_row mode 4, cta_rank_select) and the equal
+    values listed by the tie table draw from the engine in ascending order;
+    state equal to the oracle's after every sweep, equality and inequality rows."""
+    rng = np.random.RandomState(77)
+    for ineq in (False, True):
+        inst = synth.csplib022(m=8, n=20000, lo=2, hi=4, seed=51, name="long-rows-real-costs")
+        c = rng.rand(inst["n"]) * 50 + 1
+        if decimals is not None:
+            c = np.round(c, decimals)
+        inst["obj_factor"] = c.astype(np.float64)
+        if ineq:
+            inst["cmin"] = (np.asarray(inst["cmin"]) - 1).astype(np.int32)
+            inst["problem_type"] = 4  # inequalities_101
+        lockstep_engine(inst, util.params(kappa_step=0.01), [3, 4], 8, pushes_every=3)
