@@ -1142,16 +1142,28 @@ update_row(int k, int k_next, double kappa, int push, double obj_amp)
         const int fa = ia == 0 ? 0 : row_eptr[r0 + ia];
         int fb = S;
         if (S - fa > stage_cap) {
-            int lo = ia + 1, hi = r_size; // last ib with eptr[ib] - fa <= cap
-            // (row_eptr has one entry per element: the end of the last
-            // element is S, not the entry after it)
+            // last ib with eptr[ib] - fa <= cap (row_eptr has one entry per
+            // element: the end of the last element is S, not the entry after
+            // it).  The ends grow with ib, so the CTA probes a spread of
+            // candidates at once and counts those that fit: two rounds of one
+            // load each instead of a bisection of dependent loads (a
+            // 16.7 k-element row is staged in 14 chunks).  ia + 1 always fits
+            // (a column is never longer than the buffer) and every element
+            // has an entry, so ib <= ia + cap.
+            int lo = ia + 1;
+            int hi = r_size - ia > stage_cap ? ia + stage_cap : r_size;
             while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                const int end = mid < r_size ? row_eptr[r0 + mid] : S;
-                if (end - fa <= stage_cap)
-                    lo = mid;
-                else
-                    hi = mid - 1;
+                const int step = (hi - lo) / T + 1;
+                const int c = lo + tid * step;
+                bool fits = false;
+                if (c <= hi) {
+                    const int end = c < r_size ? row_eptr[r0 + c] : S;
+                    fits = end - fa <= stage_cap;
+                }
+                const int n_fit = __syncthreads_count(fits); // >= 1: lo fits
+                lo += (n_fit - 1) * step;
+                if (n_fit < T) // the candidate after the last that fits does not, or lies past hi
+                    hi = lo + step - 1 < hi ? lo + step - 1 : hi;
             }
             ib = lo;
             fb = ib < r_size ? row_eptr[r0 + ib] : S;
