@@ -317,7 +317,10 @@ bxg_default_params(bxg_params* p)
 }
 
 // context_set_solver_parameters, lib/src/private.cpp:51-172: the context
-// keeps its default for every field that fails the reference's test.
+// keeps its default for every field that fails the reference's test.  This is
+// a validation table and has to be the reference's condition by condition
+// (same accepted ranges, same fallback values), so it reads like its source;
+// everything else in this file is this repository's own design.
 void
 bxg_clamp_params(const bxg_params* in, bxg_params* out)
 {

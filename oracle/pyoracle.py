@@ -112,11 +112,16 @@ def build_oracle(force: bool = False) -> str:
     return so
 
 
-def build_ref() -> str | None:
-    """Compile _ref/libbxref*.so from /root/reference when it is present."""
+def build_ref(adapter: bool = True) -> str | None:
+    """Compile _ref/libbxref*.so from /root/reference when it is present.
+    adapter=False: only the three builds of the reference itself (they do not
+    need the engine's library, so they can compile while nvcc runs); the
+    default also links _ref/libbxref_b200.so (integration/itm_b200.cpp), which
+    needs baryonyx_b200/libbaryonyx_b200.so."""
     so = os.path.join(HERE, "_ref", "libbxref.so")
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "src")):
-        subprocess.check_call(["make", "-C", HERE, "-j", str(os.cpu_count() or 4), "ref"])
+        targets = ["ref"] if adapter else ["_ref/libbxref.so", "_ref/libbxref_fast.so", "_ref/libbxref_o3.so"]
+        subprocess.check_call(["make", "-C", HERE, "-j", str(os.cpu_count() or 4)] + targets)
     return so if os.path.exists(so) else None
 
 
