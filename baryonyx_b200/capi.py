@@ -70,7 +70,7 @@ EXPORTS = [
     "bxg_batch_begin", "bxg_batch_get_state", "bxg_batch_set_state", "bxg_batch_sweep",
     "bxg_batch_objective", "bxg_batch_solve", "bxg_batch_best", "bxg_batch_argbest",
     "bxg_batch_counters", "bxg_batch_reset_counters", "bxg_batch_path_counters", "bxg_batch_last_ms", "bxg_batch_device_ms", "bxg_batch_launches",
-    "bxg_batch_words32", "bxg_batch_begin_device", "bxg_batch_set_lane_params",
+    "bxg_batch_words32", "bxg_batch_begin_device", "bxg_batch_set_lane_params", "bxg_manual_grid",
     "bxg_population_create", "bxg_population_destroy", "bxg_population_size",
     "bxg_population_master_state", "bxg_population_generate_seeds", "bxg_population_member", "bxg_population_worker_seed",
     "bxg_population_worker_state", "bxg_population_reinit", "bxg_population_crossover",
@@ -168,6 +168,21 @@ def clamp_params(p: Params) -> Params:
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def manual_grid(p: Params, first: int = 0, capacity: int = 3125):
+    """bxg_manual_grid: points [first, first + capacity) of the reference's manual
+    auto-tuner grid as the five arrays Batch.set_lane_params takes, + the 5 x 5 tables."""
+    names = ("theta", "delta", "kappa_min", "kappa_step", "init_policy_random")
+    arrs = [np.zeros(capacity, np.float64) for _ in names]
+    tables = np.zeros((5, 5), np.float64)
+    count = C.c_int64()
+    f = lib().bxg_manual_grid
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.POINTER(C.c_int64), C.c_void_p]
+    check(f(C.byref(p), first, capacity, *[_ptr(a) for a in arrs], C.byref(count), _ptr(tables)))
+    out = {k: a[:count.value] for k, a in zip(names, arrs)}
+    out["tables"] = tables
+    return out
 
 
 class Problem:

@@ -1591,6 +1591,57 @@ bxg_batch_set_lane_params(bxg_batch* b, const double* theta, const double* delta
     return BXG_OK;
 }
 
+// The manual auto-tuner's grid (manual-optimizer.cpp:31-111, 113-160).  Five
+// dimensions of five values.  Entry 0 of a table is the caller's parameter,
+// entry 1 is step_d / 5, and entry i >= 2 is theta's entry i - 1 plus an
+// increment -- for EVERY dimension, theta's table included (that is how the
+// reference fills them, :62-87): increments 1/5, 0.1/25, 1e-2/5, 1e-7/25 and
+// 0.9/5.  The walk is an odometer over the five indices, the last one fastest.
+int
+bxg_manual_grid(const bxg_params* base, int64_t first, int64_t capacity, double* theta,
+                double* delta, double* kappa_min, double* kappa_step, double* init_policy_random,
+                int64_t* count, double* tables)
+{
+    if (!base || !count || first < 0 || capacity < 0)
+        return fail(BXG_E_INVALID, "bxg_manual_grid: bad argument");
+    constexpr int D = 5, V = 5;
+    const double len = static_cast<double>(V);
+    const double start[D] = { base->theta, base->delta, base->kappa_min, base->kappa_step,
+                              base->init_policy_random };
+    const double second[D] = { 1.0 / len, 0.1 / len, 1e-2 / len, 1e-7 / len, 0.9 / len };
+    const double step[D] = { 1.0 / len, 0.1 / (5.0 * len), 1e-2 / len, 1e-7 / (5.0 * len), 0.9 / len };
+    double tab[D][V];
+    for (int d = 0; d != D; ++d) {
+        tab[d][0] = start[d];
+        tab[d][1] = second[d];
+    }
+    // theta first: the other tables read it
+    for (int d = 0; d != D; ++d)
+        for (int i = 2; i != V; ++i)
+            tab[d][i] = tab[0][i - 1] + step[d];
+    if (tables)
+        for (int d = 0; d != D; ++d)
+            for (int i = 0; i != V; ++i)
+                tables[d * V + i] = tab[d][i];
+
+    int64_t total = 1;
+    for (int d = 0; d != D; ++d)
+        total *= V;
+    double* const out[D] = { theta, delta, kappa_min, kappa_step, init_policy_random };
+    int64_t written = 0;
+    for (int64_t p = first; p < total && written < capacity; ++p, ++written) {
+        int64_t rest = p;
+        for (int d = D - 1; d >= 0; --d) { // point p of the odometer: base-V digits, last fastest
+            const int idx = static_cast<int>(rest % V);
+            rest /= V;
+            if (out[d])
+                out[d][written] = tab[d][idx];
+        }
+    }
+    *count = written;
+    return BXG_OK;
+}
+
 int
 bxg_batch_last_ms(bxg_batch* b, float* ms)
 {

@@ -224,6 +224,22 @@ int bxg_batch_set_lane_params(bxg_batch* b, const double* theta,
                               const double* delta, const double* kappa_min,
                               const double* kappa_step,
                               const double* init_policy_random);
+/* The grid of the reference's manual auto-tuner (manual-optimizer.cpp:31-111,
+ * 113-160): five tables of five values -- entry 0 the caller's own parameter,
+ * entry 1 a fixed fraction of 1/5, the others built on theta's table as the
+ * reference builds them (:62-87, as written there) -- and the 5^5 = 3125
+ * points in the order its odometer visits them (`next()`, :98-111: the last
+ * dimension, init_policy_random, runs fastest).  Output: the five per-lane
+ * arrays bxg_batch_set_lane_params takes, `capacity` entries each (any may be
+ * NULL); points [first, first + capacity) of the walk are written, *count
+ * receives how many (0 past the end), so a grid larger than a batch is taken
+ * in slices.  `tables`, if not NULL, receives the 5 x 5 value tables (theta,
+ * delta, kappa_min, kappa_step, init_policy_random).  Host only: no device
+ * is touched. */
+int bxg_manual_grid(const bxg_params* base, int64_t first, int64_t capacity,
+                    double* theta, double* delta, double* kappa_min,
+                    double* kappa_step, double* init_policy_random,
+                    int64_t* count, double* tables);
 /* Device time of the last bxg_batch_sweep / bxg_batch_solve, CUDA events on
  * the batch's stream, milliseconds. */
 int bxg_batch_last_ms(bxg_batch* b, float* ms);

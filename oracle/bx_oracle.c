@@ -189,6 +189,73 @@ ox_clamp_params(const ox_params* in, ox_params* out)
     *out = c;
 }
 
+/* lib/src/manual-optimizer.cpp:31-111 (manual_course: the value tables, filled
+ * in the reference's statement order; `next()`: the odometer) and :113-160
+ * (optimize(): which table entry each parameter of a pass takes). */
+int
+ox_manual_grid(const ox_params* p, double* theta, double* delta, double* kappa_min,
+               double* kappa_step, double* init_policy_random, double* tables)
+{
+    enum { LENGTH = 5 };
+    double t_theta[LENGTH], t_delta[LENGTH], t_kmin[LENGTH], t_kstep[LENGTH], t_ipr[LENGTH];
+    int it[LENGTH];
+    int i, count = 0;
+    const double length = (double)LENGTH;
+
+    t_theta[0] = p->theta; /* :60-61 */
+    t_theta[1] = 1.0 / length;
+    t_delta[0] = p->delta; /* :63-64 */
+    t_delta[1] = 0.1 / length;
+    t_kmin[0] = p->kappa_min; /* :66-67 */
+    t_kmin[1] = 1e-2 / length;
+    t_kstep[0] = p->kappa_step; /* :69-70 */
+    t_kstep[1] = 1e-7 / length;
+    t_ipr[0] = p->init_policy_random; /* :72-73 */
+    t_ipr[1] = 0.9 / length;
+    for (i = 2; i != LENGTH; ++i) /* :75-76 */
+        t_theta[i] = t_theta[i - 1] + 1.0 / length;
+    for (i = 2; i != LENGTH; ++i) /* :78-80: built on theta's table */
+        t_delta[i] = t_theta[i - 1] + 0.1 / (5.0 * length);
+    for (i = 2; i != LENGTH; ++i) /* :82-83 */
+        t_kmin[i] = t_theta[i - 1] + 1e-2 / length;
+    for (i = 2; i != LENGTH; ++i) /* :85-87 */
+        t_kstep[i] = t_theta[i - 1] + 1e-7 / (5.0 * length);
+    for (i = 2; i != LENGTH; ++i) /* :89-91 */
+        t_ipr[i] = t_theta[i - 1] + 0.9 / length;
+    if (tables)
+        for (i = 0; i != LENGTH; ++i) {
+            tables[0 * LENGTH + i] = t_theta[i];
+            tables[1 * LENGTH + i] = t_delta[i];
+            tables[2 * LENGTH + i] = t_kmin[i];
+            tables[3 * LENGTH + i] = t_kstep[i];
+            tables[4 * LENGTH + i] = t_ipr[i];
+        }
+
+    for (i = 0; i != LENGTH; ++i) /* reset(), :96 */
+        it[i] = 0;
+    for (;;) {
+        int moved = 0;
+        theta[count] = t_theta[it[0]]; /* :130-137 */
+        delta[count] = t_delta[it[1]];
+        kappa_min[count] = t_kmin[it[2]];
+        kappa_step[count] = t_kstep[it[3]];
+        init_policy_random[count] = t_ipr[it[4]];
+        ++count;
+        for (i = LENGTH - 1; i >= 0; --i) { /* next(), :98-111 */
+            if (it[i] + 1 >= LENGTH)
+                it[i] = 0;
+            else {
+                ++it[i];
+                moved = 1;
+                break;
+            }
+        }
+        if (!moved)
+            break;
+    }
+    return count;
+}
+
 /* ======================================================================== */
 /* libstdc++ 13: minstd_rand0 and the distributions                         */
 /* ======================================================================== */

@@ -111,6 +111,12 @@ void ox_default_params(ox_params* p);
 /* context_set_solver_parameters, lib/src/private.cpp:51-172 */
 void ox_clamp_params(const ox_params* in, ox_params* out);
 
+/* manual_course + the walk of optimize(), lib/src/manual-optimizer.cpp:31-160:
+ * the 5^5 parameter sets of the manual auto-tuner in the order it tries them
+ * (out arrays of 3125 entries each, tables 5 x 5); returns 3125. */
+int ox_manual_grid(const ox_params* p, double* theta, double* delta, double* kappa_min,
+                   double* kappa_step, double* init_policy_random, double* tables);
+
 /* ---- libstdc++ 13 restatements ---------------------------------------- */
 uint32_t ox_minstd_next(uint32_t* state);
 int ox_bernoulli(double p, uint32_t* state);

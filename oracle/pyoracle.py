@@ -201,6 +201,34 @@ def clamp_params(p: Params) -> Params:
     return q
 
 
+_GRID_NAMES = ("theta", "delta", "kappa_min", "kappa_step", "init_policy_random")
+
+
+def manual_grid(p: Params) -> dict:
+    """ox_manual_grid: the manual auto-tuner's 3125 parameter sets + its tables."""
+    arrs = [np.zeros(3125, np.float64) for _ in _GRID_NAMES]
+    tables = np.zeros((5, 5), np.float64)
+    f = oracle().ox_manual_grid
+    f.argtypes = [C.POINTER(Params)] + [_f64p] * 5 + [_f64p]
+    n = f(C.byref(p), *arrs, tables.reshape(-1))
+    assert n == 3125
+    out = dict(zip(_GRID_NAMES, arrs))
+    out["tables"] = tables
+    return out
+
+
+def ref_manual_grid(p: Params) -> dict:
+    """bxref_manual_grid: the same from the compiled reference's manual_course."""
+    arrs = [np.zeros(4000, np.float64) for _ in _GRID_NAMES]
+    tables = np.zeros((5, 5), np.float64)
+    f = ref(False).bxref_manual_grid
+    f.argtypes = [C.POINTER(Params)] + [_f64p] * 5 + [C.c_int, _f64p]
+    n = f(C.byref(p), *arrs, 4000, tables.reshape(-1))
+    out = {k: a[:n] for k, a in zip(_GRID_NAMES, arrs)}
+    out["tables"] = tables
+    return out
+
+
 class _RunBase:
     """Common state accessors for step-level runs (oracle and reference)."""
 

@@ -72,6 +72,12 @@ void* bxref_open_pp(const char* lp_path, const bxref_params* p, int n_affect,
                     const int* variable, const int* value, char* err, int err_len);
 int bxref_affected_count(void* h);
 const char* bxref_affected(void* h, int i, int* value);
+/* The grid of the manual auto-tuner (manual-optimizer.cpp:31-160): the
+ * parameter sets its optimize() hands to itm::optimize, in its order; returns
+ * how many there are (5^5), the first `capacity` are written; tables = the
+ * 5 x 5 value tables of manual_course. */
+int bxref_manual_grid(const bxref_params* p, double* theta, double* delta, double* kappa_min,
+                      double* kappa_step, double* init_policy_random, int capacity, double* tables);
 /* The same from arrays (merged-constraint form), without the LP parser. */
 void* bxref_open_arrays(int m, int n, const int* row_ptr, const int* col,
                         const int* factor, const int* cmin, const int* cmax,

@@ -286,3 +286,35 @@ def test_parameter_sweep_lanes():
     o = op.solve(po.clamp_params(util.params(**base)), seeds[3])
     assert out["loop"][3] == o["loop"] and np.array_equal(bt.best(3), o["x"])
     bt.close(), pb.close(), op.close()
+
+
+def test_manual_grid_lanes():
+    """bxg_manual_grid -> bxg_batch_set_lane_params: a slice of the manual
+    auto-tuner's 3125 parameter sets (manual-optimizer.cpp:113-160) on the
+    lanes of one batch; every lane's whole solve equals the oracle's with that
+    lane's parameters."""
+    inst = synth.spp(m=60, n=600, lo=3, hi=6, seed=4, cost_hi=3)
+    base = dict(limit=40, pushes_limit=2, pushing_iteration_limit=4, theta=0.6, delta=0.015,
+                kappa_min=0.01, kappa_step=2e-3, init_policy_random=0.25)
+    q = to_capi(po.clamp_params(util.params(**base)))
+    grid = capi.manual_grid(q)
+    pick = np.r_[0:5, 5:3125:104]  # the first five, then a stride coprime to 5 across all dimensions
+    names = ("theta", "delta", "kappa_min", "kappa_step", "init_policy_random")
+    lanes = {k: np.ascontiguousarray(grid[k][pick]) for k in names}
+    seeds = [100 + i for i in range(len(pick))]
+    op = po.OracleProblem(inst)
+    pb = capi.Problem(inst)
+    bt = pb.batch(len(pick), q)
+    bt.set_lane_params(**lanes)
+    bt.begin(seeds)
+    out = bt.solve()
+    for l, s in enumerate(seeds):
+        over = dict(base)
+        over.update({k: float(lanes[k][l]) for k in names})
+        o = op.solve(po.clamp_params(util.params(**over)), s)
+        assert out["status"][l] == o["status"], l
+        assert out["remaining"][l] == o["remaining"], l
+        assert out["loop"][l] == o["loop"], l
+        assert out["value"][l] == o["value"], l
+        assert np.array_equal(bt.best(l), o["x"]), l
+    bt.close(), pb.close(), op.close()
