@@ -36,6 +36,24 @@ fail(int code, const std::string& msg)
     return code;
 }
 
+// No exception crosses the C boundary: an entry point whose host side
+// allocates (std::vector, std::string) runs its body inside this; an
+// allocation failure becomes BXG_E_MEMORY, anything else BXG_E_INVALID.
+template<typename Body>
+int
+guarded(const char* who, Body&& body)
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(BXG_E_MEMORY, std::string(who) + ": out of host memory");
+    } catch (const std::exception& e) {
+        return fail(BXG_E_INVALID, std::string(who) + ": " + e.what());
+    } catch (...) {
+        return fail(BXG_E_INVALID, std::string(who) + ": unexpected failure");
+    }
+}
+
 #define CUDA_TRY(expr)                                                        \
     do {                                                                      \
         cudaError_t e_ = (expr);                                              \
@@ -877,8 +895,16 @@ bxg_problem_info(const bxg_problem* pb, int* m, int* n, int* nnz, int* max_row,
     return BXG_OK;
 }
 
+static int batch_create_body(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** out);
+
 int
 bxg_batch_create(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** out)
+{
+    return guarded("bxg_batch_create", [&] { return batch_create_body(pb, n_lanes, p, out); });
+}
+
+static int
+batch_create_body(bxg_problem* pb, int n_lanes, const bxg_params* p, bxg_batch** out)
 {
     if (!pb || !p || !out || n_lanes <= 0)
         return fail(BXG_E_INVALID, "bxg_batch_create: bad argument");
@@ -1539,8 +1565,20 @@ bxg_batch_path_counters(bxg_batch* b, int64_t* updates, int64_t* cycles, int64_t
     return BXG_OK;
 }
 
+static int batch_set_lane_params_body(bxg_batch* b, const double* theta, const double* delta,
+                          const double* kappa_min, const double* kappa_step,
+                          const double* init_policy_random);
+
 int
 bxg_batch_set_lane_params(bxg_batch* b, const double* theta, const double* delta,
+                          const double* kappa_min, const double* kappa_step,
+                          const double* init_policy_random)
+{
+    return guarded("bxg_batch_set_lane_params", [&] { return batch_set_lane_params_body(b, theta, delta, kappa_min, kappa_step, init_policy_random); });
+}
+
+static int
+batch_set_lane_params_body(bxg_batch* b, const double* theta, const double* delta,
                           const double* kappa_min, const double* kappa_step,
                           const double* init_policy_random)
 {

@@ -768,8 +768,18 @@ host_pre_solve_pair(const bxg_problem& pb, engine_t& rng, double init_random,
 
 extern "C" {
 
+static int population_create_body(bxg_problem* pb, const bxg_params* p, uint64_t master_seed, int workers,
+                      bxg_population** out);
+
 int
 bxg_population_create(bxg_problem* pb, const bxg_params* p, uint64_t master_seed, int workers,
+                      bxg_population** out)
+{
+    return guarded("bxg_population_create", [&] { return population_create_body(pb, p, master_seed, workers, out); });
+}
+
+static int
+population_create_body(bxg_problem* pb, const bxg_params* p, uint64_t master_seed, int workers,
                       bxg_population** out)
 {
     if (!pb || !p || !out || workers < 1 || p->init_population_size < 1)
